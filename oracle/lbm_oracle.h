@@ -1,0 +1,119 @@
+/*
+ * lbm_oracle.h — CPU restatement of the reference's D2Q9 LBM path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may build, load or call it, and only as the checker / reported CPU baseline.
+ *
+ * PARITY UNPINNED: the reference (Rust + WGSL on wgpu) has no tests, golden vectors
+ * or fixtures for this path and cannot be built or run here (no
+ * cargo/rustc, no Vulkan ICD).  This file restates the reference's own in-tree
+ * arithmetic — the WGSL shaders and the Rust host functions cited per function —
+ * in plain C, f32, round-to-nearest, no FMA contraction (-ffp-contract=off),
+ * evaluated in WGSL source order.  It is cross-checked against an independent numpy
+ * restatement (tests/np_restatement.py) and against the derived known-answer values
+ * listed in SURVEY.md §8c.
+ */
+#ifndef LBM_ORACLE_H
+#define LBM_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "../include/lbm_wire.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* f32 <-> f16 (IEEE binary16, round-to-nearest-even), what an rgba16float store/load does. */
+uint16_t orc_f32_to_f16(float v);
+float    orc_f16_to_f32(uint16_t h);
+
+/* OpenMP threads used by the lattice passes (1 = serial; deterministic either way for
+ * masks installed before init, see orc_boundary). Returns the value in effect. */
+int orc_set_num_threads(int n);
+int orc_get_max_threads(void);
+
+/* fluid/mod.rs:31-55  LbmUniform::new */
+void orc_lbm_uniform_new(float tau, int32_t fluid_ty, int32_t soa_offset, LbmUniform *out);
+
+/* d2q9_node.rs:50 / fluid_simulator.rs:177  tau = 3*viscosity + 0.5 (f32) */
+float orc_tau_from_viscosity(float viscosity);
+
+/* fluid/lattice.rs:26-98  init_lattice_material (depth 1); ty is a FieldAnimationType */
+void orc_init_lattice_material(int32_t nx, int32_t ny, int32_t ty, LatticeInfo *out);
+
+/* Poiseuille frame whose Bulk cells become Obstacle iff
+ * splitmix64(seed ^ (y<<32 | x)) top-24-bits / 2^24 < solid_fraction. Not a reference
+ * function; restated here so the library's generator can be checked against it. */
+void orc_init_porous_material(int32_t nx, int32_t ny, uint64_t seed, float solid_fraction,
+                              LatticeInfo *out);
+
+/* assets/wgsl/lbm/init.wgsl:19-63.  macro_f16: 4 halfs per cell (RGBA16F) or NULL. */
+void orc_init(const LbmUniform *u, int32_t nx, int32_t ny, float *buf0, float *buf1,
+              LatticeInfo *info, uint16_t *macro_f16);
+
+/* assets/wgsl/lbm/collide_stream.wgsl:25-88 (+ layout_and_fn.wgsl:38-51, d2q9_fn.wgsl).
+ * rd = collide_cell (read-only), wr = stream_cell.  macro_f16 (4 halfs/cell) and
+ * macro_f32 (4 floats/cell: u.x,u.y,rho,1 before the f16 store) may each be NULL. */
+void orc_collide_stream(const LbmUniform *u, int32_t nx, int32_t ny, const float *rd, float *wr,
+                        LatticeInfo *info, uint16_t *macro_f16, float *macro_f32);
+
+/* assets/wgsl/lbm/boundary.wgsl:3-35.  Row-major serial order when 1 thread. */
+void orc_boundary(const LbmUniform *u, int32_t nx, int32_t ny, float *wr, const LatticeInfo *info);
+
+/* d2q9_node.rs:302-312  compute_by_pass: collide_stream then boundary on the same bind group. */
+void orc_step(const LbmUniform *u, int32_t nx, int32_t ny, const float *rd, float *wr,
+              LatticeInfo *info, uint16_t *macro_f16, float *macro_f32);
+
+/* n steps alternating buf0->buf1, buf1->buf0 starting with swap index `first_swap`
+ * (fluid_simulator.rs:223-231 without the particle passes). Returns the swap index
+ * the next step would use. */
+int orc_step_n(const LbmUniform *u, int32_t nx, int32_t ny, float *buf0, float *buf1,
+               LatticeInfo *info, uint16_t *macro_f16, float *macro_f32, int first_swap, int n);
+
+/* assets/wgsl/lbm/particle_update.wgsl:55-88 + func/bilinear_interpolate_3f.wgsl.
+ * Particles are visited in index order, so canvas collisions resolve to the highest index. */
+void orc_particle_update(const LbmUniform *u, const FieldUniform *field, const ParticleUniform *pu,
+                         TrajectoryParticle *particles, Pixel *canvas, const uint16_t *macro_f16);
+
+/* d2q9_node.rs:215-245 add_obstacle. Mutates the host mirror; writes the patch the
+ * reference uploads (rows [y-28, y+28) x nx) to `patch` (capacity 56*nx) and its byte
+ * offset into the info buffer. Returns the number of LatticeInfo elements in the patch. */
+size_t orc_add_obstacle(int32_t nx, int32_t ny, LatticeInfo *mirror, uint32_t x, uint32_t y,
+                        LatticeInfo *patch, uint64_t *byte_offset);
+
+/* fluid_simulator.rs:137-152 on_click guard: returns 1 and (x,y) lattice coords when the
+ * click is accepted. */
+int orc_on_click_guard(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, float px, float py,
+                       uint32_t *x, uint32_t *y);
+
+/* d2q9_node.rs:263-300 add_external_force. Emits up to `cap` (byte_offset, LatticeInfo)
+ * single-cell writes in order; returns how many. */
+size_t orc_add_external_force(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, float pos_x,
+                              float pos_y, float pre_x, float pre_y, uint64_t *byte_offsets,
+                              LatticeInfo *cells, size_t cap);
+
+/* d2q9_node.rs:65-76 FieldUniform for the LBM node (proj_ratio / ndc_pixel from
+ * util/matrix_helper.rs fullscreen_factor are render-only and left 0 here). */
+void orc_field_uniform_new(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, int32_t canvas_w,
+                           int32_t canvas_h, FieldUniform *out);
+
+/* lib.rs:247-273 particle grid extent for (canvas, count): num.x, num.y */
+void orc_particle_grid(uint32_t canvas_w, uint32_t canvas_h, int32_t count, int32_t *num_x,
+                       int32_t *num_y);
+
+/* lib.rs:275-316 init_trajectory_particles with a seeded splitmix64 stream in place of the
+ * reference's unseeded rand::rng(). Index order is the reference's push
+ * order: x outer, y inner. Writes num_x*num_y particles. */
+void orc_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas_h, int32_t num_x,
+                                   int32_t num_y, float life_time, uint64_t seed,
+                                   TrajectoryParticle *out);
+
+/* f64 sum of one distribution buffer (all 9 planes) — the "total mass" diagnostic. */
+double orc_total_mass(int32_t nx, int32_t ny, const float *buf);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
