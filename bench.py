@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — MLUPS of the D2Q9 lattice-Boltzmann step on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One bench "step" = one lattice update (pull-stream + BGK collide + bounce-back, the reference's
+compute_by_pass) of the whole lattice.  N=1: BASELINE configs[1], 4096x4096 channel + cylinders.
+N>1 (launched by torch.distributed.run, one rank per GPU): configs[2], 16384x16384 split into N
+y-slabs (strong scaling); the slabs exchange edge rows through peer memory inside the step kernel,
+there is no collective on the data path.
+
+Prints ONE JSON line (rank 0).  `value` = lattice sites updated per second / 1e6 with the state
+resident in HBM, timed with CUDA events on the library's stream, max over ranks.  `e2e` = the same
+metric through the public host API with HOST buffers inside the timed region (per step: upload of a
+56-row LatticeInfo patch from pinned memory — the reference's add_obstacle write — one step, and a
+read-back of the RGBA16F macro field into pinned memory).  `roofline` and `cpu_baseline` as
+specified in DESIGN.md.  `--impl reference` times the CPU oracle (the reference cannot be built
+here: no Rust / WebGPU) on all host cores instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_SITE = 72  # 9 f32 read + 9 f32 written
+METRIC = "MLUPS (D2Q9 f32)"
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_for(n_gpus, override):
+    if override:
+        nx, ny = override
+        name = f"D2Q9 BGK {nx}x{ny} channel + cylinder obstacles (Poiseuille preset), f32"
+    elif n_gpus == 1:
+        nx = ny = 4096
+        name = "D2Q9 BGK 4096x4096 channel + cylinder obstacle, f32, single B200 (BASELINE configs[1])"
+    else:
+        nx = ny = 16384
+        name = f"D2Q9 16384x16384 strong scaling, {n_gpus} y-slabs with peer-memory edge rows (BASELINE configs[2])"
+    return nx, ny, name
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._mark = None
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self, t0=None, t1=None):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+        win = [s for s in self.samples if t0 is None or t0 <= s[0] <= t1] or self.samples
+        if not win:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        bits = 0
+        for s in win:
+            bits |= s[2]
+        reasons = [name for b, name in self.REASONS.items() if bits & b]
+        return {"sm_mhz": statistics.median(s[1] for s in win), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(win)}
+
+
+def cpu_leg(nx, ny, budget_s, min_steps=3):
+    """Times the CPU oracle (OpenMP, all host cores) on rows of the same workload. Returns a dict."""
+    import numpy as np
+
+    import oracle as orc
+
+    cores = orc.lib().orc_get_max_threads()
+    info = orc.init_lattice_material(nx, ny, 4)
+    tau = float(np.float32(3.0) * np.float32(0.02) + np.float32(0.5))
+    sim = orc.OracleSim(nx, ny, info, orc.uniform_new(tau, 0, (nx * ny) & 0x7FFFFFFF), threads=cores)
+    sim.step(1)
+    t0 = time.perf_counter()
+    n = 0
+    while n < min_steps or time.perf_counter() - t0 < budget_s:
+        sim.step(1)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": nx * ny * n / dt / 1e6, "unit": "MLUPS", "cores": cores, "kind": "port",
+            "sample": f"{nx}x{ny} lattice, {n} steps in {dt:.1f} s (CPU restatement of the reference WGSL, OpenMP)"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own step on the host cores.  The reference (Rust + WGSL via
+    wgpu) cannot be built in this image, so this is the oracle port; each step updates a bounded
+    band of the workload's lattice so that K+W steps end within a few minutes."""
+    if rank != 0:
+        return
+    import numpy as np
+
+    import oracle as orc
+
+    nx, ny, name = workload_for(args.gpus, args.lattice)
+    cores = orc.lib().orc_get_max_threads()
+    tau = float(np.float32(3.0) * np.float32(0.02) + np.float32(0.5))
+    # calibrate on a thin band, then size the band for ~150 s total
+    rows = 64
+    info = orc.init_lattice_material(nx, rows, 4)
+    sim = orc.OracleSim(nx, rows, info, orc.uniform_new(tau, 0, nx * rows), threads=cores)
+    sim.step(1)
+    t0 = time.perf_counter()
+    sim.step(3)
+    per_row = (time.perf_counter() - t0) / 3 / rows
+    total = args.steps + args.warmup
+    rows = int(max(64, min(ny, 150.0 / total / per_row)))
+    info = orc.init_lattice_material(nx, rows, 4)
+    sim = orc.OracleSim(nx, rows, info, orc.uniform_new(tau, 0, nx * rows), threads=cores)
+    sim.step(args.warmup)
+    t0 = time.perf_counter()
+    sim.step(args.steps)
+    dt = time.perf_counter() - t0
+    v = nx * rows * args.steps / dt / 1e6
+    sample = f"{nx}x{rows} band of the {nx}x{ny} lattice per step, {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": name, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lattice", type=int, nargs=2, default=None, metavar=("NX", "NY"), help="override the workload")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (0 = skip)")
+    ap.add_argument("--generic", action="store_true", help="time the one-thread-per-cell kernel instead")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torch.distributed.run with {args.gpus} ranks (see docstring)")
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    import numpy as np
+    import torch
+
+    import simuverse_b200 as sb
+    from simuverse_b200 import wire as W
+    from simuverse_b200.slabs import SlabRank
+
+    if sb.lib.lbm_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: simuverse_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nx, ny, name = workload_for(args.gpus, args.lattice)
+    setting = sb.SettingObj(animation_type=W.POISEUILLE)
+    flags = sb.FLAG_KERNEL_GENERIC if args.generic else 0
+    canvas = (nx * 2, ny * 2)
+    if world == 1:
+        node = sb.D2Q9Node(canvas, setting, lattice=(nx, ny), device_preset=W.POISEUILLE, device=local_rank, flags=flags)
+        slab = None
+    else:
+        slab = SlabRank(canvas, setting, lattice=(nx, ny), dist=dist, device=local_rank, device_preset=W.POISEUILLE,
+                        flags=flags)
+        node = slab.node
+
+    def barrier():
+        node.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    node.step_n(args.warmup)
+    barrier()
+    launches0 = node.launch_count
+    t0 = time.perf_counter()
+    node.step_n(args.steps)          # K launches, CUDA events recorded around them on the library's stream
+    ms = node.last_step_n_ms()       # synchronises on the end event
+    barrier()
+    t1 = time.perf_counter()
+    launches = node.launch_count - launches0
+    clocks = sampler.stop(t0, t1)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sites = nx * ny
+    value = sites * args.steps / (ms * 1e-3) / 1e6
+    mass = slab.total_mass() if slab is not None else node.total_mass()
+
+    # ---- e2e through the host API with host buffers (N=1 only: the field read is single-slab)
+    e2e = None
+    if world == 1 and args.e2e_steps > 0:
+        rows = 56
+        patch_t = torch.empty(rows * nx * 16, dtype=torch.uint8).pin_memory()
+        macro_t = torch.empty(sites * 8, dtype=torch.uint8).pin_memory()
+        patch = patch_t.numpy().view(W.LATTICE_INFO_DTYPE)
+        macro = macro_t.numpy()
+        y_lo = ny // 2 - 28
+        full = node.read_lattice_info()
+        patch[:] = full[y_lo * nx:(y_lo + rows) * nx]  # re-upload of unchanged rows: same traffic, same mask
+        del full
+        import ctypes as C
+
+        from simuverse_b200._capi import MACRO_RGBA16F, check, lib
+        from simuverse_b200.wire import ptr
+
+        def e2e_step():
+            check(lib.lbm_write_lattice_info(node._h, y_lo * nx * 16, ptr(patch), patch.nbytes), node._h)
+            check(lib.lbm_step_n(node._h, 1), node._h)
+            check(lib.lbm_read_macro(node._h, MACRO_RGBA16F, ptr(macro)), node._h)
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        ta = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        tb = time.perf_counter()
+        e2e = {"value": sites * args.e2e_steps / (tb - ta) / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(patch.nbytes), "d2h_bytes_per_step": int(macro.nbytes),
+               "steps": args.e2e_steps,
+               "what": "per step: lbm_write_lattice_info(56-row patch, pinned host) + lbm_step_n(1) + "
+                       "lbm_read_macro(RGBA16F field -> pinned host), synchronous"}
+        _ = C
+    elif world > 1:
+        e2e = None
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        per_launch_s = ms * 1e-3 / args.steps
+        achieved = BYTES_PER_SITE * (sites / world) / per_launch_s / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "lattice": [nx, ny], "tau": 0.56, "l2": "inputs_larger_than_l2",
+                       "kernel": "k_step_generic" if args.generic else "k_step_vec", "state": "A/B ping-pong SoA planes",
+                       "total_mass_after": mass},
+            "clocks": clocks,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": BYTES_PER_SITE * sites // world,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps,
+        }
+        if e2e is not None:
+            out["e2e"] = e2e
+        if world == 1 and args.cpu_seconds > 0:
+            out["cpu_baseline"] = cpu_leg(nx, ny, args.cpu_seconds)
+        print(json.dumps(out))
+    barrier()  # no slab may unmap memory a neighbour still reads
+    node.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+/*
+ * lbm_b200.h — C ABI of the B200-native D2Q9 lattice-Boltzmann step.
+ *
+ * This is the drop-in boundary for the one hot path of jinleili/simuverse: what a
+ * Rust `-sys` crate (rust/lbm-b200-sys), a ctypes binding (simuverse_b200/_capi.py) or
+ * any other FFI binds in place of the wgpu objects owned by the reference's
+ * `D2Q9Node` (simuverse/src/fluid/d2q9_node.rs:13-27).  Plain pointers and sizes
+ * only; no torch / CUDA types in any signature.  Every function returns an
+ * LbmStatus (0 = OK) and never unwinds across the boundary (the reference panics:
+ * util/shader.rs:81,123).
+ *
+ * Correspondence with the reference (file:line relative to the reference tree):
+ *
+ *   lbm_create                 D2Q9Node::new buffer/texture creation     d2q9_node.rs:31-209
+ *   lbm_write_uniform          queue.write_buffer(lbm_uniform_buf)       fluid_simulator.rs:188-192
+ *   lbm_write_field_uniform    create_uniform_buffer(field_uniform_data) d2q9_node.rs:65-83
+ *   lbm_write_lattice_info     queue.write_buffer(info_buf, off, bytes)  d2q9_node.rs:244,250-254,298
+ *   lbm_reset                  reset_node.compute (init.wgsl)            d2q9_node.rs:211-213, init.wgsl:19-63
+ *   lbm_step                   compute_by_pass(cpass, swap_index)        d2q9_node.rs:302-312
+ *                              = collide_stream.wgsl:25-88 then boundary.wgsl:3-35, fused
+ *   lbm_step_n                 the frame loop's alternation 0,1,0,1,...  fluid_simulator.rs:223-231
+ *   lbm_read_macro             macro_tex (RGBA16F) contents              d2q9_node.rs:91-104
+ *   lbm_particles_update       particle_update_node.compute_by_pass      fluid_simulator.rs:225,229
+ *                              = particle_update.wgsl:55-88
+ *   lbm_read_distributions /   (no reference equivalent: can_read_back=false,
+ *   lbm_write_distributions     d2q9_node.rs:112-117) — parity tests and checkpoint/restore
+ *
+ * Host-side (CPU, no GPU needed) mirrors of the reference's Rust helpers live at the
+ * bottom: lbm_uniform_new, lbm_init_lattice_material, lbm_obstacle_patch, ...
+ *
+ * Threading: a handle is not thread-safe; one caller thread, like the reference's
+ * single-threaded app (app_handler.rs:34).  All calls on a handle are stream-ordered;
+ * reads synchronise before returning.
+ *
+ * Multi-GPU: one handle per GPU (one process per GPU under torch.distributed, or several
+ * handles in one process).  Handle `rank` of `world` owns the y-slab
+ * rows [ny*rank/world, ny*(rank+1)/world).  Neighbouring slabs are wired with
+ * lbm_ipc_export / lbm_ipc_attach; after that the edge rows of every step read and write
+ * the neighbours' memory directly over NVLink and steps are ordered by device-side flags.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+#include "lbm_wire.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_B200_ABI_VERSION 1
+
+typedef struct LbmSim LbmSim; /* opaque */
+
+typedef enum LbmStatus {
+    LBM_OK = 0,
+    LBM_ERR_INVALID_ARG = 1,
+    LBM_ERR_CUDA = 2,          /* a CUDA runtime call failed; see lbm_last_error */
+    LBM_ERR_NO_DEVICE = 3,     /* no usable CUDA device: there is NO CPU fallback */
+    LBM_ERR_OUT_OF_MEMORY = 4,
+    LBM_ERR_UNSUPPORTED = 5,   /* e.g. a uniform whose e-vectors are not D2Q9 */
+    LBM_ERR_STATE = 6          /* call order violated (e.g. step before uniform upload) */
+} LbmStatus;
+
+/* LbmDesc.flags */
+#define LBM_FLAG_MACRO_EVERY_STEP 0x1u /* write the RGBA16F macro texture in every step, like
+                                          collide_stream.wgsl:74 (needed by the tracer particles).
+                                          Off: the field is produced on demand by lbm_read_macro. */
+#define LBM_FLAG_KERNEL_GENERIC   0x2u /* force the one-thread-per-cell kernel (A/B testing) */
+
+/* lbm_read_macro formats */
+#define LBM_MACRO_F32_PLANES 0 /* 3 planes (u.x, u.y, rho) of rows*nx f32, before the f16 store */
+#define LBM_MACRO_RGBA16F    1 /* rows*nx texels of 4 halfs (u.x, u.y, rho, 1), the reference texture */
+
+/* lbm_generate_lattice_info presets beyond FieldAnimationType */
+#define LBM_PRESET_POROUS 100 /* SURVEY.md §8d config 5 */
+
+typedef struct LbmDesc {
+    uint32_t struct_size;        /* = sizeof(LbmDesc) */
+    int32_t  nx, ny;             /* global lattice (D2Q9Node::lattice, d2q9_node.rs:39-43) */
+    int32_t  lattice_pixel_size; /* d2q9_node.rs:38 */
+    int32_t  canvas_w, canvas_h; /* particle canvas in pixels; 0 = nx*lattice_pixel_size etc. */
+    int32_t  device;             /* CUDA device ordinal; -1 = current device */
+    int32_t  rank, world;        /* y-slab decomposition; world <= 1 means the whole lattice */
+    uint32_t flags;              /* LBM_FLAG_* */
+    int32_t  max_particles;      /* capacity of the particle buffer; 0 = no tracer particles */
+} LbmDesc;
+
+/* Opaque blob a slab publishes to its two y-neighbours (exchange it with any transport,
+ * e.g. torch.distributed.all_gather). */
+typedef struct LbmIpcBlob {
+    uint8_t bytes[256];
+} LbmIpcBlob;
+
+/* ------------------------------------------------------------------ lifecycle */
+int         lbm_abi_version(void);
+int         lbm_device_count(void);                 /* 0 when no GPU / driver */
+int         lbm_create(const LbmDesc *desc, LbmSim **out);
+void        lbm_destroy(LbmSim *sim);
+const char *lbm_last_error(const LbmSim *sim);      /* sim may be NULL: last lbm_create failure */
+const char *lbm_status_string(int status);
+
+/* ------------------------------------------------------------------ uploads */
+int lbm_write_uniform(LbmSim *sim, const LbmUniform *u);
+int lbm_write_field_uniform(LbmSim *sim, const FieldUniform *f);
+/* byte_offset/nbytes address the GLOBAL info buffer (nx*ny*16 bytes, row-major); a slab keeps
+ * the part that intersects its rows and one halo row each side, so every rank may be handed
+ * the same call. */
+int lbm_write_lattice_info(LbmSim *sim, uint64_t byte_offset, const void *src, uint64_t nbytes);
+/* Same content as lbm_init_lattice_material / lbm_init_porous_material, generated on the
+ * device (no host array, no upload).  kind: FieldAnimationType or LBM_PRESET_POROUS. */
+int lbm_generate_lattice_info(LbmSim *sim, int32_t kind, uint64_t seed, float solid_fraction);
+
+/* ------------------------------------------------------------------ compute */
+int lbm_reset(LbmSim *sim);                         /* init.wgsl; next step reads buffer 0 */
+int lbm_step(LbmSim *sim, int32_t swap_index);      /* reads buffer swap_index, writes the other */
+int lbm_step_n(LbmSim *sim, int32_t n);             /* n steps alternating from lbm_swap_index */
+int lbm_swap_index(const LbmSim *sim);              /* buffer the next lbm_step_n step reads */
+int lbm_sync(LbmSim *sim);
+
+/* ------------------------------------------------------------------ read-back / restore */
+/* Rows owned by this handle: [*y0, *y0 + *rows). */
+int lbm_slab_rows(const LbmSim *sim, int32_t *y0, int32_t *rows);
+/* dst/src: 9 planes of rows*nx f32, plane-major like the reference buffer
+ * (d2q9_fn.wgsl:13-17) restricted to the owned rows. which = 0 or 1. */
+int lbm_read_distributions(LbmSim *sim, int32_t which, float *dst);
+int lbm_write_distributions(LbmSim *sim, int32_t which, const float *src);
+int lbm_read_macro(LbmSim *sim, int32_t format, void *dst);
+/* Owned rows of the info buffer including device-side block_iter/material mutation
+ * (collide_stream.wgsl:55-62). dst: rows*nx LatticeInfo. */
+int lbm_read_lattice_info(LbmSim *sim, LatticeInfo *dst);
+/* f64 sum over the owned rows of all 9 planes of buffer `which`. */
+int lbm_total_mass(LbmSim *sim, int32_t which, double *out);
+
+/* ------------------------------------------------------------------ tracer particles */
+int lbm_write_particle_uniform(LbmSim *sim, const ParticleUniform *pu);
+int lbm_particles_write(LbmSim *sim, const TrajectoryParticle *src, uint64_t count);
+int lbm_particles_update(LbmSim *sim);              /* particle_update.wgsl:55-88 */
+int lbm_particles_read(LbmSim *sim, TrajectoryParticle *dst, uint64_t count);
+int lbm_canvas_clear(LbmSim *sim);
+int lbm_canvas_read(LbmSim *sim, Pixel *dst);       /* canvas_w*canvas_h pixels */
+
+/* ------------------------------------------------------------------ multi-GPU wiring */
+int lbm_ipc_export(LbmSim *sim, LbmIpcBlob *out);
+/* up = slab owning row y0-1 (rank-1 mod world), down = slab owning row y0+rows. */
+int lbm_ipc_attach(LbmSim *sim, const LbmIpcBlob *up, const LbmIpcBlob *down);
+
+/* ------------------------------------------------------------------ timing / introspection */
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+uint64_t lbm_launch_count(const LbmSim *sim);
+/* Device time of the last lbm_step_n call in milliseconds, measured with CUDA events on the
+ * handle's own stream (torch.cuda.Event only sees torch's current stream). */
+int lbm_last_step_n_ms(LbmSim *sim, float *ms);
+/* Raw stream handle (cudaStream_t) for callers that want to order their own work. */
+void *lbm_stream(LbmSim *sim);
+
+/* ------------------------------------------------------------------ host-side mirrors (CPU only) */
+/* fluid/mod.rs:31-55 LbmUniform::new */
+void  lbm_uniform_new(float tau, int32_t fluid_ty, int32_t soa_offset, LbmUniform *out);
+/* d2q9_node.rs:50, fluid_simulator.rs:177 */
+float lbm_tau_from_viscosity(float viscosity);
+/* d2q9_node.rs:65-76 (proj_ratio / ndc_pixel are render-only and left 0) */
+void  lbm_field_uniform_new(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, int32_t canvas_w,
+                            int32_t canvas_h, FieldUniform *out);
+/* fluid/lattice.rs:26-98 */
+int   lbm_init_lattice_material(int32_t nx, int32_t ny, int32_t ty, LatticeInfo *out);
+int   lbm_init_porous_material(int32_t nx, int32_t ny, uint64_t seed, float solid_fraction,
+                               LatticeInfo *out);
+/* fluid_simulator.rs:137-152 on_click guard; returns 1 when accepted */
+int   lbm_on_click_guard(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, float px, float py,
+                         uint32_t *x, uint32_t *y);
+/* d2q9_node.rs:215-245 add_obstacle: updates the CPU mirror, fills the 56-row patch and its
+ * byte offset; returns the element count of the patch. */
+uint64_t lbm_obstacle_patch(int32_t nx, int32_t ny, LatticeInfo *mirror, uint32_t x, uint32_t y,
+                            LatticeInfo *patch, uint64_t *byte_offset);
+/* d2q9_node.rs:263-300 add_external_force: the single-cell writes it issues, in order */
+uint64_t lbm_external_force_cells(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, float pos_x,
+                                  float pos_y, float pre_x, float pre_y, uint64_t *byte_offsets,
+                                  LatticeInfo *cells, uint64_t cap);
+/* lib.rs:247-264 */
+void  lbm_particle_grid(uint32_t canvas_w, uint32_t canvas_h, int32_t count, int32_t *num_x,
+                        int32_t *num_y);
+/* lib.rs:275-316 with a seeded stream instead of rand::rng() */
+void  lbm_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas_h, int32_t num_x,
+                                    int32_t num_y, float life_time, uint64_t seed,
+                                    TrajectoryParticle *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,684 @@
+// lbm_b200.cu — C ABI (include/lbm_b200.h) over the CUDA kernels: handle, memory layout,
+// launch logic.  There is deliberately no CPU code path for any compute entry point: with no
+// CUDA device lbm_create fails with LBM_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "lbm_kernels.cuh"
+#include "lbm_particles.cuh"
+#include "lbm_step_vec.cuh"
+
+using namespace lbm;
+
+namespace {
+
+std::string g_create_error;
+
+// What a slab publishes to its neighbours (fits LbmIpcBlob).
+struct IpcPayload {
+    uint32_t magic;
+    int32_t pid;
+    int32_t device;
+    int32_t rank, world;
+    int32_t nx, ny, y0, h, pitch;
+    uint64_t plane;           // floats
+    uint64_t f_off[2];        // byte offsets of f[0], f[1] in the arena
+    uint64_t flag_off;        // byte offset of the progress flags
+    uint64_t arena_bytes;
+    uint64_t local_ptr;       // arena address in the exporting process (same-process attach)
+    cudaIpcMemHandle_t handle;
+};
+static_assert(sizeof(IpcPayload) <= sizeof(LbmIpcBlob), "blob too small");
+constexpr uint32_t kIpcMagic = 0x4c424d31u; // "LBM1"
+
+}  // namespace
+
+struct LbmSim {
+    LbmDesc d{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    SlabParams P{};
+    char *arena = nullptr;      // f[0], f[1], sync flags (one allocation, one IPC handle)
+    size_t arena_bytes = 0;
+    size_t f_off[2] = {0, 0};
+    size_t flag_off = 0;
+    double *d_mass = nullptr;
+    float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
+    bool have_uniform = false;
+    bool have_info = false;
+    LbmUniform u{};
+    FieldUniform field{};
+    ParticleUniform pu{};
+    bool have_pu = false;
+    TrajectoryParticle *particles = nullptr;
+    uint64_t n_particles = 0;
+    Pixel *canvas = nullptr;
+    int canvas_w = 0, canvas_h = 0;
+    int swap = 0;
+    uint64_t launches = 0;
+    // neighbours (multi-slab)
+    void *peer_base[2] = {nullptr, nullptr}; // IPC-opened arenas (up, down); nullptr when same-process
+    bool peer_ipc[2] = {false, false};
+    StepSync sync{};
+    bool attached = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(LbmSim *s, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (s) s->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(s, e__ == cudaErrorMemoryAllocation ? LBM_ERR_OUT_OF_MEMORY : LBM_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_launch(LbmSim *s, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    s->launches++;
+    return LBM_OK;
+}
+
+dim3 grid2d(int nx, int rows, dim3 block) { return dim3((nx + block.x - 1) / block.x, (rows + block.y - 1) / block.y, 1); }
+
+int derive_rows(LbmSim *s, int l0, int l1) {
+    l0 = std::max(l0, 0);
+    l1 = std::min(l1, s->P.h);
+    if (l0 >= l1) return LBM_OK;
+    dim3 block(64, 4);
+    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1);
+    return check_launch(s, "k_derive");
+}
+
+bool uniform_is_d2q9(const LbmUniform *u) {
+    static const float ex[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
+    static const float ey[9] = {0, 0, -1, 0, 1, -1, -1, 1, 1};
+    static const int inv[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    for (int i = 0; i < 9; i++) {
+        if (u->e_w_max[i][0] != ex[i] || u->e_w_max[i][1] != ey[i]) return false;
+        if (u->inversed_direction[i][0] != inv[i]) return false;
+    }
+    return true;
+}
+
+int ensure_scratch32(LbmSim *s) {
+    if (s->scratch32) return LBM_OK;
+    CU(cudaMalloc(&s->scratch32, sizeof(float) * 3 * (size_t)s->P.h * s->P.nx));
+    return LBM_OK;
+}
+
+int launch_step(LbmSim *s, int rb) {
+    int rc = LBM_OK;
+    if (s->d.flags & LBM_FLAG_KERNEL_GENERIC) {
+        const bool multi = s->d.world > 1;
+        if (multi) {
+            k_wait<<<1, 32, 0, s->stream>>>(s->sync);
+            if ((rc = check_launch(s, "k_wait"))) return rc;
+        }
+        dim3 block(64, 4);
+        k_step_generic<0><<<grid2d(s->P.nx, s->P.h, block), block, 0, s->stream>>>(s->P, rb, 0, s->P.h);
+        if ((rc = check_launch(s, "k_step_generic"))) return rc;
+        if (multi) {
+            k_signal<<<1, 32, 0, s->stream>>>(s->sync);
+            if ((rc = check_launch(s, "k_signal"))) return rc;
+        }
+    } else {
+        cudaError_t e = launch_step_vec(s->P, s->sync, rb, s->stream);
+        if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_step_vec failed: %s", cudaGetErrorString(e));
+        s->launches++;
+    }
+    s->sync.step_no++;
+    return LBM_OK;
+}
+
+int ready_to_step(LbmSim *s) {
+    if (!s->have_uniform) return fail(s, LBM_ERR_STATE, "lbm_write_uniform has not been called");
+    if (!s->have_info) return fail(s, LBM_ERR_STATE, "no lattice info uploaded or generated");
+    if (s->d.world > 1 && !s->attached) return fail(s, LBM_ERR_STATE, "slab of a %d-slab lattice is not attached to its neighbours (lbm_ipc_attach)", s->d.world);
+    return LBM_OK;
+}
+
+}  // namespace
+
+// =================================================================== lifecycle
+
+extern "C" int lbm_abi_version(void) { return LBM_B200_ABI_VERSION; }
+
+extern "C" int lbm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" const char *lbm_status_string(int st) {
+    switch (st) {
+        case LBM_OK: return "ok";
+        case LBM_ERR_INVALID_ARG: return "invalid argument";
+        case LBM_ERR_CUDA: return "CUDA error";
+        case LBM_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+        case LBM_ERR_OUT_OF_MEMORY: return "out of device memory";
+        case LBM_ERR_UNSUPPORTED: return "unsupported";
+        case LBM_ERR_STATE: return "call order violated";
+        default: return "unknown status";
+    }
+}
+
+extern "C" const char *lbm_last_error(const LbmSim *s) { return s ? s->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void lbm_destroy(LbmSim *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int k = 0; k < 2; k++)
+        if (s->peer_ipc[k] && s->peer_base[k]) cudaIpcCloseMemHandle(s->peer_base[k]);
+    cudaFree(s->arena);
+    cudaFree(s->P.cls);
+    cudaFree(s->P.nbr);
+    cudaFree(s->P.info);
+    cudaFree(s->P.macro16);
+    cudaFree(s->scratch32);
+    cudaFree(s->d_mass);
+    cudaFree(s->particles);
+    cudaFree(s->canvas);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int create_impl(LbmSim *s, const LbmDesc *desc) {
+    s->d = *desc;
+    if (s->d.world < 1) s->d.world = 1;
+    const LbmDesc &d = s->d;
+    if (d.nx < 3 || d.ny < 3) return fail(s, LBM_ERR_INVALID_ARG, "lattice %dx%d too small (need >= 3x3)", d.nx, d.ny);
+    if (d.rank < 0 || d.rank >= d.world) return fail(s, LBM_ERR_INVALID_ARG, "rank %d outside world %d", d.rank, d.world);
+    if (d.world > 1 && d.ny / d.world < 2) return fail(s, LBM_ERR_INVALID_ARG, "ny=%d gives slabs thinner than 2 rows for world=%d", d.ny, d.world);
+    if (d.lattice_pixel_size < 1) return fail(s, LBM_ERR_INVALID_ARG, "lattice_pixel_size must be >= 1");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(s, LBM_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (d.device >= ndev) return fail(s, LBM_ERR_INVALID_ARG, "device %d of %d", d.device, ndev);
+    if (d.device >= 0) { CU(cudaSetDevice(d.device)); s->device = d.device; }
+    else CU(cudaGetDevice(&s->device));
+
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+
+    SlabParams &P = s->P;
+    P.nx = d.nx;
+    P.ny = d.ny;
+    P.y0 = (int)((int64_t)d.ny * d.rank / d.world);
+    const int y1 = (int)((int64_t)d.ny * (d.rank + 1) / d.world);
+    P.h = y1 - P.y0;
+    P.pitch = (int)align_up((size_t)d.nx, 32);
+    P.plane = align_up((size_t)P.h * P.pitch, 32);
+
+    const size_t fbytes = align_up(sizeof(float) * 9 * P.plane, 256);
+    s->f_off[0] = 0;
+    s->f_off[1] = fbytes;
+    s->flag_off = 2 * fbytes;
+    s->arena_bytes = 2 * fbytes + 256;
+    CU(cudaMalloc(&s->arena, s->arena_bytes));
+    CU(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
+    P.f[0] = reinterpret_cast<float *>(s->arena + s->f_off[0]);
+    P.f[1] = reinterpret_cast<float *>(s->arena + s->f_off[1]);
+    // world == 1: rows -1 / h wrap onto the own rows h-1 / 0 (layout_and_fn.wgsl:45-49)
+    for (int b = 0; b < 2; b++) {
+        P.up[b] = P.f[b] + (size_t)(P.h - 1) * P.pitch;
+        P.dn[b] = P.f[b];
+    }
+    P.up_plane = P.dn_plane = P.plane;
+
+    const size_t cells = (size_t)P.h * P.pitch;
+    CU(cudaMalloc(&P.cls, cells));
+    CU(cudaMalloc(&P.nbr, cells));
+    CU(cudaMemsetAsync(P.cls, CLS_SOLID, cells, s->stream));
+    CU(cudaMemsetAsync(P.nbr, 0, cells, s->stream));
+    const size_t info_bytes = sizeof(LatticeInfo) * (size_t)(P.h + 2) * P.nx;
+    CU(cudaMalloc(&P.info, info_bytes));
+    CU(cudaMemsetAsync(P.info, 0, info_bytes, s->stream));
+    if (d.flags & LBM_FLAG_MACRO_EVERY_STEP) {
+        CU(cudaMalloc(&P.macro16, sizeof(__half) * 4 * (size_t)P.h * P.nx));
+        CU(cudaMemsetAsync(P.macro16, 0, sizeof(__half) * 4 * (size_t)P.h * P.nx, s->stream));
+    }
+    CU(cudaMalloc(&s->d_mass, sizeof(double)));
+
+    s->canvas_w = d.canvas_w > 0 ? d.canvas_w : d.nx * d.lattice_pixel_size;
+    s->canvas_h = d.canvas_h > 0 ? d.canvas_h : d.ny * d.lattice_pixel_size;
+    if (d.max_particles > 0) {
+        if (d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "tracer particles are single-slab only");
+        CU(cudaMalloc(&s->particles, sizeof(TrajectoryParticle) * (size_t)d.max_particles));
+        CU(cudaMemsetAsync(s->particles, 0, sizeof(TrajectoryParticle) * (size_t)d.max_particles, s->stream));
+        CU(cudaMalloc(&s->canvas, sizeof(Pixel) * (size_t)s->canvas_w * s->canvas_h));
+        CU(cudaMemsetAsync(s->canvas, 0, sizeof(Pixel) * (size_t)s->canvas_w * s->canvas_h, s->stream));
+    }
+    // default FieldUniform (d2q9_node.rs:65-76); lbm_write_field_uniform may replace it
+    lbm_field_uniform_new(d.nx, d.ny, (uint32_t)d.lattice_pixel_size, s->canvas_w, s->canvas_h, &s->field);
+
+    s->sync.flags = reinterpret_cast<unsigned int *>(s->arena + s->flag_off);
+    s->sync.world = d.world;
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_create(const LbmDesc *desc, LbmSim **out) {
+    if (!desc || !out) return fail(nullptr, LBM_ERR_INVALID_ARG, "null argument");
+    if (desc->struct_size != sizeof(LbmDesc))
+        return fail(nullptr, LBM_ERR_INVALID_ARG, "LbmDesc.struct_size %u != %zu", desc->struct_size, sizeof(LbmDesc));
+    *out = nullptr;
+    LbmSim *s = new LbmSim();
+    int rc = create_impl(s, desc);
+    if (rc != LBM_OK) {
+        g_create_error = s->err;
+        lbm_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return LBM_OK;
+}
+
+// =================================================================== uploads
+
+extern "C" int lbm_write_uniform(LbmSim *s, const LbmUniform *u) {
+    if (!s || !u) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!uniform_is_d2q9(u))
+        return fail(s, LBM_ERR_UNSUPPORTED, "LbmUniform e_w_max / inversed_direction are not the D2Q9 set of fluid/mod.rs:39-52");
+    s->u = *u;
+    s->P.k.omega = u->omega;
+    s->P.k.fluid_ty = u->fluid_ty;
+    for (int i = 0; i < 9; i++) {
+        s->P.k.w[i] = u->e_w_max[i][2];
+        s->P.k.mx[i] = u->e_w_max[i][3];
+    }
+    s->have_uniform = true;
+    return LBM_OK;
+}
+
+extern "C" int lbm_write_field_uniform(LbmSim *s, const FieldUniform *f) {
+    if (!s || !f) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (f->lattice_size[0] != s->d.nx || f->lattice_size[1] != s->d.ny)
+        return fail(s, LBM_ERR_INVALID_ARG, "FieldUniform.lattice_size %dx%d does not match the handle's %dx%d",
+                    f->lattice_size[0], f->lattice_size[1], s->d.nx, s->d.ny);
+    s->field = *f;
+    return LBM_OK;
+}
+
+extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const void *src, uint64_t nbytes) {
+    if (!s || (!src && nbytes)) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    const SlabParams &P = s->P;
+    const uint64_t row_bytes = (uint64_t)P.nx * sizeof(LatticeInfo);
+    const uint64_t total = row_bytes * (uint64_t)P.ny;
+    if (byte_offset > total || nbytes > total - byte_offset)
+        return fail(s, LBM_ERR_INVALID_ARG, "write of %llu bytes at %llu exceeds the %llu-byte info buffer",
+                    (unsigned long long)nbytes, (unsigned long long)byte_offset, (unsigned long long)total);
+    if (nbytes == 0) return LBM_OK;
+    CU(cudaSetDevice(s->device));
+    const uint64_t lo = byte_offset, hi = byte_offset + nbytes;
+    int touched_lo = P.h + 2, touched_hi = -1; // halo-indexed rows r = 0..h+1
+    // (halo-indexed local row range, global first row) of the three pieces this slab keeps
+    struct Piece { int r0, rows, gy; };
+    const Piece pieces[3] = {
+        {0, 1, (P.y0 - 1 + P.ny) % P.ny},
+        {1, P.h, P.y0},
+        {P.h + 1, 1, (P.y0 + P.h) % P.ny},
+    };
+    for (const Piece &pc : pieces) {
+        const uint64_t g0 = (uint64_t)pc.gy * row_bytes, g1 = g0 + (uint64_t)pc.rows * row_bytes;
+        const uint64_t a = std::max(lo, g0), b = std::min(hi, g1);
+        if (a >= b) continue;
+        char *dst = reinterpret_cast<char *>(P.info) + (uint64_t)pc.r0 * row_bytes + (a - g0);
+        CU(cudaMemcpyAsync(dst, static_cast<const char *>(src) + (a - lo), b - a, cudaMemcpyHostToDevice, s->stream));
+        touched_lo = std::min(touched_lo, pc.r0 + (int)((a - g0) / row_bytes));
+        touched_hi = std::max(touched_hi, pc.r0 + (int)((b - 1 - g0) / row_bytes));
+    }
+    // the source may be pageable host memory the caller reuses right away
+    CU(cudaStreamSynchronize(s->stream));
+    if (touched_hi >= 0) {
+        s->have_info = true;
+        // owned row l = r - 1; a changed row alters the neighbour bits of rows l-1 .. l+1
+        int rc = derive_rows(s, touched_lo - 2, touched_hi + 1);
+        if (rc) return rc;
+    }
+    return LBM_OK;
+}
+
+extern "C" int lbm_generate_lattice_info(LbmSim *s, int32_t kind, uint64_t seed, float solid_fraction) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (kind != FIELD_ANIMATION_POISEUILLE && kind != FIELD_ANIMATION_LID_DRIVEN_CAVITY &&
+        kind != FIELD_ANIMATION_CUSTOM && kind != LBM_PRESET_POROUS)
+        return fail(s, LBM_ERR_INVALID_ARG, "unknown preset %d", kind);
+    CU(cudaSetDevice(s->device));
+    dim3 block(64, 4);
+    k_generate<<<grid2d(s->P.nx, s->P.h + 2, block), block, 0, s->stream>>>(s->P, kind, seed, solid_fraction);
+    int rc = check_launch(s, "k_generate");
+    if (rc) return rc;
+    s->have_info = true;
+    return derive_rows(s, 0, s->P.h);
+}
+
+// =================================================================== compute
+
+extern "C" int lbm_reset(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->have_uniform) return fail(s, LBM_ERR_STATE, "lbm_write_uniform has not been called");
+    if (!s->have_info) return fail(s, LBM_ERR_STATE, "no lattice info uploaded or generated");
+    CU(cudaSetDevice(s->device));
+    dim3 block(64, 4);
+    k_init<<<grid2d(s->P.nx, s->P.h, block), block, 0, s->stream>>>(s->P);
+    int rc = check_launch(s, "k_init");
+    if (rc) return rc;
+    s->swap = 0;
+    // init.wgsl:51-59 may have turned armed force cells back into bulk
+    return derive_rows(s, 0, s->P.h);
+}
+
+extern "C" int lbm_step(LbmSim *s, int32_t swap_index) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (swap_index != 0 && swap_index != 1) return fail(s, LBM_ERR_INVALID_ARG, "swap_index must be 0 or 1");
+    int rc = ready_to_step(s);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    rc = launch_step(s, swap_index);
+    if (rc) return rc;
+    s->swap = swap_index ^ 1;
+    return LBM_OK;
+}
+
+extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
+    if (!s || n < 0) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    int rc = ready_to_step(s);
+    if (rc) return rc;
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->ev0, s->stream));
+    for (int i = 0; i < n; i++) {
+        rc = launch_step(s, s->swap);
+        if (rc) return rc;
+        s->swap ^= 1;
+    }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->timed = true;
+    return LBM_OK;
+}
+
+extern "C" int lbm_swap_index(const LbmSim *s) { return s ? s->swap : -1; }
+
+extern "C" int lbm_sync(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// =================================================================== read-back / restore
+
+extern "C" int lbm_slab_rows(const LbmSim *s, int32_t *y0, int32_t *rows) {
+    if (!s) return LBM_ERR_INVALID_ARG;
+    if (y0) *y0 = s->P.y0;
+    if (rows) *rows = s->P.h;
+    return LBM_OK;
+}
+
+extern "C" int lbm_read_distributions(LbmSim *s, int32_t which, float *dst) {
+    if (!s || !dst || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    const SlabParams &P = s->P;
+    const size_t n = (size_t)P.h * P.nx;
+    for (int i = 0; i < 9; i++)
+        CU(cudaMemcpy2DAsync(dst + i * n, sizeof(float) * P.nx, P.f[which] + i * P.plane, sizeof(float) * P.pitch,
+                             sizeof(float) * P.nx, P.h, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_write_distributions(LbmSim *s, int32_t which, const float *src) {
+    if (!s || !src || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    const SlabParams &P = s->P;
+    const size_t n = (size_t)P.h * P.nx;
+    for (int i = 0; i < 9; i++)
+        CU(cudaMemcpy2DAsync(P.f[which] + i * P.plane, sizeof(float) * P.pitch, src + i * n, sizeof(float) * P.nx,
+                             sizeof(float) * P.nx, P.h, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (format != LBM_MACRO_F32_PLANES && format != LBM_MACRO_RGBA16F) return fail(s, LBM_ERR_INVALID_ARG, "unknown macro format %d", format);
+    CU(cudaSetDevice(s->device));
+    const SlabParams &P = s->P;
+    const size_t n = (size_t)P.h * P.nx;
+    if (format == LBM_MACRO_RGBA16F && P.macro16) {
+        // written by the step itself (LBM_FLAG_MACRO_EVERY_STEP)
+        CU(cudaMemcpyAsync(dst, P.macro16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        return LBM_OK;
+    }
+    // On demand: the buffer the last step read is still intact (A/B ping-pong), so pulling from it
+    // again yields exactly the (rho, u) that step computed (collide_stream.wgsl:43-74).
+    int rc = ready_to_step(s);
+    if (rc) return rc;
+    SlabParams Q = P;
+    __half *tmp16 = nullptr;
+    if (format == LBM_MACRO_F32_PLANES) {
+        rc = ensure_scratch32(s);
+        if (rc) return rc;
+        Q.macro32 = s->scratch32;
+        Q.macro16 = nullptr;
+    } else {
+        CU(cudaMalloc(&tmp16, sizeof(__half) * 4 * n));
+        Q.macro16 = tmp16;
+        Q.macro32 = nullptr;
+    }
+    dim3 block(64, 4);
+    k_step_generic<1><<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(Q, s->swap ^ 1, 0, P.h);
+    rc = check_launch(s, "k_step_generic<macro>");
+    if (rc == LBM_OK) {
+        cudaError_t e = (format == LBM_MACRO_F32_PLANES)
+                            ? cudaMemcpyAsync(dst, Q.macro32, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream)
+                            : cudaMemcpyAsync(dst, tmp16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) rc = fail(s, LBM_ERR_CUDA, "macro read-back failed: %s", cudaGetErrorString(e));
+    }
+    if (tmp16) cudaFree(tmp16);
+    return rc;
+}
+
+extern "C" int lbm_read_lattice_info(LbmSim *s, LatticeInfo *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    const SlabParams &P = s->P;
+    CU(cudaMemcpyAsync(dst, P.info + P.nx, sizeof(LatticeInfo) * (size_t)P.h * P.nx, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_total_mass(LbmSim *s, int32_t which, double *out) {
+    if (!s || !out || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->d_mass, 0, sizeof(double), s->stream));
+    k_mass<<<148 * 4, 256, 0, s->stream>>>(s->P, which, s->d_mass);
+    int rc = check_launch(s, "k_mass");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, s->d_mass, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// =================================================================== tracer particles
+
+extern "C" int lbm_write_particle_uniform(LbmSim *s, const ParticleUniform *pu) {
+    if (!s || !pu) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (pu->num[0] < 0 || pu->num[1] < 0 || (int64_t)pu->num[0] * pu->num[1] > (int64_t)s->d.max_particles)
+        return fail(s, LBM_ERR_INVALID_ARG, "particle grid %dx%d exceeds max_particles=%d", pu->num[0], pu->num[1], s->d.max_particles);
+    s->pu = *pu;
+    s->have_pu = true;
+    return LBM_OK;
+}
+
+extern "C" int lbm_particles_write(LbmSim *s, const TrajectoryParticle *src, uint64_t count) {
+    if (!s || !src) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (count > (uint64_t)s->d.max_particles) return fail(s, LBM_ERR_INVALID_ARG, "%llu particles exceed max_particles=%d", (unsigned long long)count, s->d.max_particles);
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(s->particles, src, sizeof(TrajectoryParticle) * count, cudaMemcpyHostToDevice, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->n_particles = count;
+    return LBM_OK;
+}
+
+extern "C" int lbm_particles_update(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->particles) return fail(s, LBM_ERR_STATE, "handle was created with max_particles = 0");
+    if (!s->have_pu) return fail(s, LBM_ERR_STATE, "lbm_write_particle_uniform has not been called");
+    if (!s->P.macro16) return fail(s, LBM_ERR_STATE, "tracer particles read the macro texture: create the handle with LBM_FLAG_MACRO_EVERY_STEP");
+    CU(cudaSetDevice(s->device));
+    cudaError_t e = launch_particle_update(s->P, s->field, s->pu, s->particles, s->canvas, s->stream);
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_particle_update failed: %s", cudaGetErrorString(e));
+    s->launches++;
+    return LBM_OK;
+}
+
+extern "C" int lbm_particles_read(LbmSim *s, TrajectoryParticle *dst, uint64_t count) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (count > (uint64_t)s->d.max_particles) return fail(s, LBM_ERR_INVALID_ARG, "count exceeds max_particles");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(dst, s->particles, sizeof(TrajectoryParticle) * count, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_canvas_clear(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->canvas) return fail(s, LBM_ERR_STATE, "handle was created with max_particles = 0");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemsetAsync(s->canvas, 0, sizeof(Pixel) * (size_t)s->canvas_w * s->canvas_h, s->stream));
+    return LBM_OK;
+}
+
+extern "C" int lbm_canvas_read(LbmSim *s, Pixel *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->canvas) return fail(s, LBM_ERR_STATE, "handle was created with max_particles = 0");
+    CU(cudaSetDevice(s->device));
+    CU(cudaMemcpyAsync(dst, s->canvas, sizeof(Pixel) * (size_t)s->canvas_w * s->canvas_h, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// =================================================================== multi-GPU wiring
+
+extern "C" int lbm_ipc_export(LbmSim *s, LbmIpcBlob *out) {
+    if (!s || !out) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    memset(out, 0, sizeof(*out));
+    IpcPayload p{};
+    p.magic = kIpcMagic;
+    p.pid = (int32_t)getpid_portable();
+    p.device = s->device;
+    p.rank = s->d.rank;
+    p.world = s->d.world;
+    p.nx = s->P.nx; p.ny = s->P.ny; p.y0 = s->P.y0; p.h = s->P.h; p.pitch = s->P.pitch;
+    p.plane = s->P.plane;
+    p.f_off[0] = s->f_off[0]; p.f_off[1] = s->f_off[1];
+    p.flag_off = s->flag_off;
+    p.arena_bytes = s->arena_bytes;
+    p.local_ptr = (uint64_t)(uintptr_t)s->arena;
+    CU(cudaIpcGetMemHandle(&p.handle, s->arena));
+    memcpy(out->bytes, &p, sizeof(p));
+    return LBM_OK;
+}
+
+extern "C" int lbm_ipc_attach(LbmSim *s, const LbmIpcBlob *up, const LbmIpcBlob *down) {
+    if (!s || !up || !down) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (s->d.world < 2) return fail(s, LBM_ERR_STATE, "a single-slab lattice has no neighbours to attach");
+    if (s->attached) return fail(s, LBM_ERR_STATE, "already attached");
+    CU(cudaSetDevice(s->device));
+    const LbmIpcBlob *blobs[2] = {up, down};
+    const int want_rank[2] = {(s->d.rank - 1 + s->d.world) % s->d.world, (s->d.rank + 1) % s->d.world};
+    char *base[2] = {nullptr, nullptr};
+    IpcPayload pl[2];
+    for (int k = 0; k < 2; k++) {
+        memcpy(&pl[k], blobs[k]->bytes, sizeof(IpcPayload));
+        const IpcPayload &p = pl[k];
+        if (p.magic != kIpcMagic) return fail(s, LBM_ERR_INVALID_ARG, "neighbour blob %d is not an LbmIpcBlob", k);
+        if (p.rank != want_rank[k] || p.world != s->d.world || p.nx != s->P.nx || p.ny != s->P.ny || p.pitch != s->P.pitch)
+            return fail(s, LBM_ERR_INVALID_ARG, "neighbour blob %d describes rank %d of %d (%dx%d), expected rank %d of %d (%dx%d)",
+                        k, p.rank, p.world, p.nx, p.ny, want_rank[k], s->d.world, s->P.nx, s->P.ny);
+        if (p.pid == (int32_t)getpid_portable()) {
+            // same process: plain peer access
+            if (p.device != s->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, s->device, p.device));
+                if (!can) return fail(s, LBM_ERR_UNSUPPORTED, "device %d cannot access peer device %d", s->device, p.device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(p.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(s, LBM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", p.device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            base[k] = reinterpret_cast<char *>((uintptr_t)p.local_ptr);
+        } else if (k == 1 && pl[0].pid == p.pid && pl[0].rank == p.rank && s->peer_ipc[0]) {
+            base[k] = static_cast<char *>(s->peer_base[0]); // world == 2: both neighbours are the same slab
+        } else {
+            void *ptr = nullptr;
+            CU(cudaIpcOpenMemHandle(&ptr, p.handle, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_base[k] = ptr;
+            s->peer_ipc[k] = true;
+            base[k] = static_cast<char *>(ptr);
+        }
+    }
+    SlabParams &P = s->P;
+    for (int b = 0; b < 2; b++) {
+        // up neighbour's last row; down neighbour's first row
+        P.up[b] = reinterpret_cast<float *>(base[0] + pl[0].f_off[b]) + (size_t)(pl[0].h - 1) * pl[0].pitch;
+        P.dn[b] = reinterpret_cast<float *>(base[1] + pl[1].f_off[b]);
+    }
+    P.up_plane = pl[0].plane;
+    P.dn_plane = pl[1].plane;
+    s->sync.peer_flags[0] = reinterpret_cast<unsigned int *>(base[0] + pl[0].flag_off);
+    s->sync.peer_flags[1] = reinterpret_cast<unsigned int *>(base[1] + pl[1].flag_off);
+    s->attached = true;
+    return LBM_OK;
+}
+
+// =================================================================== introspection
+
+extern "C" uint64_t lbm_launch_count(const LbmSim *s) { return s ? s->launches : 0; }
+
+extern "C" int lbm_last_step_n_ms(LbmSim *s, float *ms) {
+    if (!s || !ms) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->timed) return fail(s, LBM_ERR_STATE, "lbm_step_n has not been called");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->ev1));
+    CU(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return LBM_OK;
+}
+
+extern "C" void *lbm_stream(LbmSim *s) { return s ? (void *)s->stream : nullptr; }

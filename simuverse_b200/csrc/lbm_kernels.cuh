@@ -1,0 +1,154 @@
+// lbm_kernels.cuh — kernels of the D2Q9 path other than the vectorised step
+// (which lives in lbm_step_vec.cuh): generic step, init, class/neighbour derivation,
+// device-side preset generation, mass reduction, on-demand macro field.
+#pragma once
+
+#include "lbm_device.cuh"
+
+namespace lbm {
+
+// ------------------------------------------------------------------ generic step
+// One thread per cell over rows [l0, l1). Serves as the A/B-testing baseline
+// (LBM_FLAG_KERNEL_GENERIC) and as the on-demand macro pass (MODE 1).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_step_generic(const __grid_constant__ SlabParams P, int rb, int l0, int l1) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = l0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.nx || l >= l1) return;
+    update_cell<MODE>(P, rb, x, l);
+}
+
+// ------------------------------------------------------------------ init.wgsl:19-63
+__global__ void __launch_bounds__(256) k_init(const __grid_constant__ SlabParams P) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.nx || l >= P.h) return;
+    LatticeInfo *ip = P.info + (size_t)(l + 1) * P.nx + x;
+    LatticeInfo in = *ip;
+    const size_t cl = (size_t)l * P.pitch + x;
+    float *b0 = P.f[0] + cl, *b1 = P.f[1] + cl;
+    const bool solid = in.material == 2 || in.material == 4;
+    if (solid) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) { b0[i * P.plane] = 0.0f; b1[i * P.plane] = 0.0f; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; i++) { b0[i * P.plane] = P.k.w[i]; b1[i * P.plane] = 0.0f; }
+        if (P.k.fluid_ty == 0) { // isPoiseuilleFlow(): bias along +x (init.wgsl:39-43)
+            const float temp = fmul(P.k.w[3], 0.5f);
+            const float f1 = fadd(P.k.w[1], temp);
+            b0[1 * P.plane] = f1; b0[3 * P.plane] = temp;
+            b1[1 * P.plane] = f1; b1[3 * P.plane] = temp;
+        }
+    }
+    if ((in.material == 3 || in.material == 6) && in.block_iter > 0) { // init.wgsl:51-59
+        in.block_iter = 0; in.material = 1; in.vx = 0.0f; in.vy = 0.0f;
+        *ip = in;
+    }
+    if (P.macro16 || P.macro32) store_macro(P, x, l, 0.0f, 0.0f, 0.0f, 1.0f); // init.wgsl:62
+}
+
+// ------------------------------------------------------------------ class / neighbour planes
+// Derived from the authoritative LatticeInfo buffer for owned rows [l0, l1).
+__global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabParams P, int l0, int l1) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int l = l0 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.nx || l >= l1) return;
+    const LatticeInfo *row = P.info + (size_t)(l + 1) * P.nx;
+    const int m = row[x].material;
+    const int y = P.y0 + l;
+    uint8_t nb = 0;
+    // boundary.wgsl:19 — only strictly interior cells ever receive a bounce-back
+    if (x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1) {
+#pragma unroll
+        for (int i = 1; i < 9; i++) {
+            const int mm = row[(ptrdiff_t)kEy[i] * P.nx + x + kEx[i]].material;
+            if (mm == 2 || mm == 4) nb |= (uint8_t)(1u << (i - 1));
+        }
+    }
+    uint8_t c;
+    if (m == 2 || m == 4) c = CLS_SOLID;
+    else if (m == 3 || m == 6) c = CLS_ACCEL;
+    else c = nb ? CLS_FLUID_NB : CLS_FLUID;
+    const size_t cl = (size_t)l * P.pitch + x;
+    P.cls[cl] = c;
+    P.nbr[cl] = nb;
+}
+
+// ------------------------------------------------------------------ preset generators
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ bool in_disc(float px, float py, float r) { // fluid/mod.rs:57-59
+    return __fsqrt_rn(fadd(fmul(px, px), fmul(py, py))) <= r;
+}
+
+// fluid/lattice.rs:26-98 evaluated per cell; fills halo rows too (r = 0 .. h+1).
+__global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SlabParams P, int kind, uint64_t seed,
+                                                  float solid_fraction) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.nx || r >= P.h + 2) return;
+    int y = P.y0 - 1 + r;
+    if (y < 0) y += P.ny;
+    if (y >= P.ny) y -= P.ny;
+    const int nx = P.nx, ny = P.ny;
+    int material = 1;
+    float vx = 0.0f;
+    if (kind == FIELD_ANIMATION_CUSTOM) {
+        if (x == 0 || x == nx - 1 || y == 0 || y == ny - 1) material = 2;
+    } else if (kind == FIELD_ANIMATION_LID_DRIVEN_CAVITY) {
+        if (x == 0 || x == nx - 1 || y == ny - 1) material = 2;
+        else if (y == 0) material = 7;
+        else if (y == 1) { material = 6; vx = 0.13f; }
+    } else { // Poiseuille frame (also the porous preset)
+        if (y == 0 || y == ny - 1) material = 2;
+        else if (x == 0 || x == nx - 1) material = 7;
+        else if (x == 1) { material = 3; vx = 0.12f; }
+        else if (x == nx - 2) material = 5;
+        else if (kind == FIELD_ANIMATION_POISEUILLE) {
+            const float R = 28.0f;
+            const float s0x = fsub(fdiv((float)nx, 7.0f), R), s0y = fdiv((float)ny, 2.0f);
+            const float s1x = fdiv((float)nx, 5.0f), s1y = fdiv((float)ny, 4.0f);
+            const float s2x = s1x, s2y = fmul((float)ny, 0.75f);
+            const float px = (float)x, py = (float)y;
+            if (in_disc(fsub(px, s0x), fsub(py, s0y), R) || in_disc(fsub(px, s1x), fsub(py, s1y), R) ||
+                in_disc(fsub(px, s2x), fsub(py, s2y), R))
+                material = 4;
+        } else { // LBM_PRESET_POROUS
+            const uint64_t hsh = splitmix64(seed ^ (((uint64_t)(uint32_t)y << 32) | (uint64_t)(uint32_t)x));
+            const float u = fdiv((float)(hsh >> 40), 16777216.0f);
+            if (u < solid_fraction) material = 4;
+        }
+    }
+    LatticeInfo o;
+    o.material = material; o.block_iter = -1; o.vx = vx; o.vy = 0.0f;
+    P.info[(size_t)r * nx + x] = o;
+}
+
+// ------------------------------------------------------------------ total mass (f64)
+__global__ void __launch_bounds__(256) k_mass(const __grid_constant__ SlabParams P, int b, double *out) {
+    double s = 0.0;
+    const size_t n = (size_t)P.h * P.nx;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+        const size_t l = c / P.nx, x = c - l * P.nx;
+        const float *p = P.f[b] + l * P.pitch + x;
+#pragma unroll
+        for (int i = 0; i < 9; i++) s += (double)p[i * P.plane];
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = ws[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_down_sync(0xffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
+}
+
+}  // namespace lbm

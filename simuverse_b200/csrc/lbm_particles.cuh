@@ -1,0 +1,93 @@
+// lbm_particles.cuh — tracer-particle advection through the macroscopic field.
+// Restates particle_update.wgsl:55-88, its src_3f/update_canvas helpers (:15-53) and
+// func/bilinear_interpolate_3f.wgsl:1-12.  One thread per particle; the field is the
+// RGBA16F macro texture the step writes (f16-quantised, like textureLoad in the reference).
+#pragma once
+
+#include "lbm_device.cuh"
+
+namespace lbm {
+
+struct Tex3 { float x, y, z; };
+
+__device__ __forceinline__ Tex3 src_3f(const __half *macro16, int nx, int ny, int u, int v) {
+    const int nu = min(max(u, 0), nx - 1); // particle_update.wgsl:16-17
+    const int nv = min(max(v, 0), ny - 1);
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(macro16) + ((size_t)nv * nx + nu));
+    const __half2 a = *reinterpret_cast<const __half2 *>(&t.x);
+    const __half2 b = *reinterpret_cast<const __half2 *>(&t.y);
+    Tex3 r;
+    r.x = __low2float(a);
+    r.y = __high2float(a);
+    r.z = __low2float(b);
+    return r;
+}
+
+// WGSL f32 -> i32: truncate toward zero, saturating (cvt.rzi.s32.f32 saturates; NaN -> 0)
+__device__ __forceinline__ int f2i(float v) { return __float2int_rz(v); }
+
+__global__ void __launch_bounds__(256) k_particle_update(const __half *__restrict__ macro16, int nx, int ny,
+                                                         const __grid_constant__ FieldUniform field,
+                                                         const __grid_constant__ ParticleUniform pu, int poiseuille,
+                                                         TrajectoryParticle *particles, Pixel *canvas) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (gx >= pu.num[0] || gy >= pu.num[1]) return;
+    const size_t p_index = (size_t)gx + (size_t)gy * pu.num[0];
+    TrajectoryParticle p = particles[p_index];
+    if (p.life_time <= 0.1f) {
+        p.fade = 0.0f;
+        p.pos[0] = p.pos_initial[0];
+        p.pos[1] = p.pos_initial[1];
+        p.life_time = pu.life_time;
+    } else {
+        p.life_time = fsub(p.life_time, 1.0f);
+        if (p.fade < 1.0f) {
+            if (p.fade < 0.95f) p.fade = fadd(p.fade, 0.1f); else p.fade = 1.0f;
+        }
+        const float ijx = fsub(fdiv(p.pos[0], field.lattice_pixel_size[0]), 0.5f);
+        const float ijy = fsub(fdiv(p.pos[1], field.lattice_pixel_size[1]), 0.5f);
+        const int minX = f2i(floorf(ijx)), minY = f2i(floorf(ijy));
+        const float fx = fsub(ijx, (float)minX), fy = fsub(ijy, (float)minY);
+        const Tex3 a = src_3f(macro16, nx, ny, minX, minY);
+        const Tex3 b = src_3f(macro16, nx, ny, minX, minY + 1);
+        const Tex3 c = src_3f(macro16, nx, ny, minX + 1, minY);
+        const Tex3 d = src_3f(macro16, nx, ny, minX + 1, minY + 1);
+        const float wa = fmul(fsub(1.0f, fx), fsub(1.0f, fy));
+        const float wb = fmul(fsub(1.0f, fx), fy);
+        const float wc = fmul(fx, fsub(1.0f, fy));
+        const float wd = fmul(fx, fy);
+        const float vx = fadd(fadd(fadd(fmul(a.x, wa), fmul(b.x, wb)), fmul(c.x, wc)), fmul(d.x, wd));
+        const float vy = fadd(fadd(fadd(fmul(a.y, wa), fmul(b.y, wb)), fmul(c.y, wc)), fmul(d.y, wd));
+        p.pos[0] = fadd(p.pos[0], fmul(vx, pu.speed_factor));
+        p.pos[1] = fadd(p.pos[1], fmul(vy, pu.speed_factor));
+        // update_canvas (particle_update.wgsl:32-53); concurrent writers to one pixel race in the
+        // reference too (last writer wins)
+        const float speed = fadd(fabsf(vx), fabsf(vy));
+        const bool skip = (!poiseuille && speed < 0.0f) || (poiseuille && speed < 0.015f);
+        if (!skip && canvas) {
+            const int px = f2i(p.pos[0]) - pu.point_size / 2;
+            const int py = f2i(p.pos[1]) - pu.point_size / 2;
+            Pixel pix;
+            pix.alpha = p.fade; pix.velocity_x = vx; pix.velocity_y = vy;
+            for (int dx = 0; dx < pu.point_size; dx++)
+                for (int dy = 0; dy < pu.point_size; dy++) {
+                    const int cx = px + dx, cy = py + dy;
+                    if (cx >= 0 && cx < field.canvas_size[0] && cy >= 0 && cy < field.canvas_size[1])
+                        canvas[(size_t)cx + (size_t)field.canvas_size[0] * cy] = pix;
+                }
+        }
+    }
+    particles[p_index] = p;
+}
+
+inline cudaError_t launch_particle_update(const SlabParams &P, const FieldUniform &field, const ParticleUniform &pu,
+                                          TrajectoryParticle *particles, Pixel *canvas, cudaStream_t stream) {
+    if (pu.num[0] <= 0 || pu.num[1] <= 0) return cudaSuccess;
+    dim3 block(16, 16); // particle_update.wgsl:55
+    dim3 grid((pu.num[0] + 15) / 16, (pu.num[1] + 15) / 16);
+    k_particle_update<<<grid, block, 0, stream>>>(P.macro16, P.nx, P.h, field, pu, P.k.fluid_ty == 0, particles, canvas);
+    return cudaGetLastError();
+}
+
+}  // namespace lbm

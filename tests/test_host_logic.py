@@ -1,0 +1,159 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol
+include/lbm_b200.h declares, the host mirrors of the reference's Rust helpers agree with the
+oracle bit for bit, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import simuverse_b200 as sb
+from simuverse_b200 import _capi
+from simuverse_b200 import wire as W
+from simuverse_b200.wire import ptr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "lbm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lbm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_functions()
+    assert len(names) >= 40
+    raw = C.CDLL(sb.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/lbm_b200.h but not exported"
+        assert n in _capi.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert sorted(_capi.PROTOTYPES) == names
+    assert sb.lib.lbm_abi_version() == 1
+
+
+def test_wire_sizes_match_header():
+    text = open(os.path.join(ROOT, "include", "lbm_wire.h")).read()
+    for name, size in [("LbmUniform", 304), ("FieldUniform", 48), ("LatticeInfo", 16), ("ParticleUniform", 48),
+                       ("TrajectoryParticle", 24), ("Pixel", 12)]:
+        assert f"sizeof({name}) == {size}" in text
+        assert C.sizeof(getattr(W, name)) == size
+    assert C.sizeof(_capi.LbmDesc) == 44 and C.sizeof(_capi.LbmIpcBlob) == 256
+
+
+def test_uniform_new_bytes_match_oracle(orc):
+    for tau, ty in [(0.56, 0), (0.8, 1), (1.7, 0)]:
+        a = sb.lbm_uniform_new(tau, ty, 225000)
+        b = orc.uniform_new(tau, ty, 225000)
+        assert bytes(a) == bytes(b)
+    assert sb.lib.lbm_tau_from_viscosity(float(np.float32(0.02))) == orc.tau_from_viscosity(0.02)
+
+
+@pytest.mark.parametrize("nx,ny", [(600, 375), (128, 128), (131, 77), (37, 19), (300, 1000)])
+@pytest.mark.parametrize("ty", [W.POISEUILLE, W.LID_DRIVEN_CAVITY, W.CUSTOM, 0])
+def test_init_lattice_material_matches_oracle(orc, nx, ny, ty):
+    a = sb.init_lattice_material(nx, ny, ty)
+    b = orc.init_lattice_material(nx, ny, ty)
+    assert a.tobytes() == b.tobytes()
+
+
+def test_porous_material_matches_oracle(orc):
+    a = sb.init_porous_material(257, 130, seed=0x5EED, solid_fraction=0.30)
+    b = orc.init_porous_material(257, 130, seed=0x5EED, solid_fraction=0.30)
+    assert a.tobytes() == b.tobytes()
+    inner = a.reshape(130, 257)["material"][1:-1, 2:-2]
+    frac = (inner == W.OBSTACLE).mean()
+    assert 0.27 < frac < 0.33
+    c = sb.init_porous_material(257, 130, seed=7, solid_fraction=0.30)
+    assert c.tobytes() != a.tobytes()
+
+
+def test_on_click_guard_and_obstacle_patch_match_oracle(orc):
+    nx, ny, lps = 600, 375, 2
+    for pos in [(0.0, 10.0), (-1.0, 5.0), (55.9, 300.0), (56.0, 56.0), (600.0, 400.0), (1139.0, 689.0), (1140.0, 400.0),
+                (700.5, 690.0)]:
+        x, y = C.c_uint32(), C.c_uint32()
+        ok = sb.lib.lbm_on_click_guard(nx, ny, lps, pos[0], pos[1], C.byref(x), C.byref(y))
+        want = orc.on_click_guard(nx, ny, lps, *pos)
+        assert (ok == 1) == (want is not None)
+        if want:
+            assert (x.value, y.value) == want
+    mirror_a = sb.init_lattice_material(nx, ny, W.POISEUILLE)
+    mirror_b = mirror_a.copy()
+    for (x, y) in [(300, 200), (305, 190), (40, 28), (569, 344)]:
+        patch = np.zeros(56 * nx, W.LATTICE_INFO_DTYPE)
+        off = C.c_uint64()
+        n = sb.lib.lbm_obstacle_patch(nx, ny, ptr(mirror_a), x, y, ptr(patch), C.byref(off))
+        woff, wpatch = orc.add_obstacle(nx, ny, mirror_b, x, y)
+        assert n == wpatch.size == 56 * nx and off.value == woff == nx * (y - 28) * 16
+        assert patch[:n].tobytes() == wpatch.tobytes()
+        assert mirror_a.tobytes() == mirror_b.tobytes()
+    assert (mirror_a["material"] == W.OBSTACLE).sum() > 7374 + 3 * 2400
+
+
+def test_external_force_cells_match_oracle(orc):
+    nx, ny, lps = 600, 375, 2
+    cases = [((400.0, 300.0), (380.0, 310.0)), ((10.0, 10.0), (300.0, 300.0)), ((500.5, 200.25), (500.5, 200.25)),
+             ((1198.0, 700.0), (1100.0, 745.0)), ((3.0, 3.0), (1.0, 2.0))]
+    for pos, pre in cases:
+        offs = np.zeros(4096, np.uint64)
+        cells = np.zeros(4096, W.LATTICE_INFO_DTYPE)
+        n = sb.lib.lbm_external_force_cells(nx, ny, lps, pos[0], pos[1], pre[0], pre[1], ptr(offs), ptr(cells), 4096)
+        woffs, wcells = orc.add_external_force(nx, ny, lps, pos, pre)
+        assert n == woffs.size
+        np.testing.assert_array_equal(offs[:n], woffs)
+        assert cells[:n].tobytes() == wcells.tobytes()
+        if n:
+            assert (cells[:n]["material"] == 6).all() and (cells[:n]["block_iter"] == 90).all()
+            assert np.hypot(cells[0]["vx"], cells[0]["vy"]) <= 0.12 + 1e-6
+
+
+def test_particle_seeding_matches_oracle(orc):
+    assert sb.particle_grid((1200, 750), 10000) == orc.particle_grid(1200, 750, 10000) == (127, 80)
+    assert sb.particle_grid((16384, 16384), 1000000) == orc.particle_grid(16384, 16384, 1000000) == (1000, 1000)
+    for life in (90.0, 1.0, 0.0):
+        a = sb.init_trajectory_particles((1200, 750), (127, 80), life, 0x5EED)
+        b = orc.init_trajectory_particles(1200, 750, 127, 80, life, 0x5EED)
+        assert a.tobytes() == b.tobytes()
+    a = sb.init_trajectory_particles((1200, 750), (127, 80), 90.0, 0x5EED)
+    assert (a["life_time"] >= 0).all() and (a["life_time"] <= 90).all() and (a["fade"] == 0).all()
+    np.testing.assert_array_equal(a["pos"], a["pos_initial"])
+
+
+def test_field_uniform_matches_oracle(orc):
+    f = W.FieldUniform()
+    sb.lib.lbm_field_uniform_new(600, 375, 2, 1200, 750, C.byref(f))
+    assert bytes(f) == bytes(orc.field_uniform_new(600, 375, 2, 1200, 750))
+    assert f.speed_ty == 1 and tuple(f.lattice_pixel_size) == (2.0, 2.0)
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    """On a box without a CUDA device the compute path must refuse to exist."""
+    if sb.lib.lbm_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(sb.LbmError) as e:
+        sb.D2Q9Node((1200, 750), sb.SettingObj())
+    assert e.value.status == _capi.ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_bad_descriptors():
+    d = _capi.LbmDesc()
+    h = C.c_void_p()
+    d.struct_size = 4
+    assert sb.lib.lbm_create(C.byref(d), C.byref(h)) == _capi.ERR_INVALID_ARG
+    d.struct_size = C.sizeof(_capi.LbmDesc)
+    d.nx, d.ny, d.lattice_pixel_size, d.world = 2, 2, 2, 1
+    assert sb.lib.lbm_create(C.byref(d), C.byref(h)) == _capi.ERR_INVALID_ARG
+    assert b"too small" in sb.lib.lbm_last_error(None)
+    assert sb.lib.lbm_create(None, C.byref(h)) == _capi.ERR_INVALID_ARG
+    assert sb.lib.lbm_step(None, 0) == _capi.ERR_INVALID_ARG  # null handle never crashes
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "simuverse_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"

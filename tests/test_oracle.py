@@ -1,0 +1,223 @@
+"""Pins the CPU oracle: derived known answers, the committed golden vectors,
+and bit-agreement with the independent numpy restatement.  CPU only."""
+import ctypes as C
+import zlib
+
+import numpy as np
+import pytest
+
+import np_restatement as R
+from helpers import assert_bits_equal, golden_cases, tau_default
+from simuverse_b200 import wire as W
+
+
+def test_uniform_constants(orc):
+    u = orc.uniform_new(tau_default(), 0, 600 * 375)
+    assert C.sizeof(u) == 304
+    assert abs(u.tau - 0.56) < 1e-7 and u.omega == np.float32(1.0) / np.float32(u.tau)
+    w = [u.e_w_max[i][2] for i in range(9)]
+    assert w == [np.float32(0.444444)] + [np.float32(0.111111)] * 4 + [np.float32(0.0277777)] * 4
+    assert [u.e_w_max[i][3] for i in range(9)] == [np.float32(0.6)] + [np.float32(0.2222)] * 4 + [np.float32(0.1111)] * 4
+    assert [u.inversed_direction[i][0] for i in range(9)] == [0, 3, 4, 1, 2, 7, 8, 5, 6]
+    e = [(u.e_w_max[i][0], u.e_w_max[i][1]) for i in range(9)]
+    assert e == [(0, 0), (1, 0), (0, -1), (-1, 0), (0, 1), (1, -1), (-1, -1), (-1, 1), (1, 1)]
+    for i in range(9):  # inverse really is the opposite vector
+        j = u.inversed_direction[i][0]
+        assert (e[j][0], e[j][1]) == (-e[i][0], -e[i][1])
+
+
+@pytest.mark.parametrize("nx,ny,hist,crc", [
+    (600, 375, {1: 214934, 2: 1200, 3: 373, 4: 7374, 5: 373, 7: 746}, 0xF8EFC262),
+    (4096, 4096, {1: 16745276, 2: 8192, 3: 4094, 4: 7372, 5: 4094, 7: 8188}, 0x63A17811),
+])
+def test_mask_known_answers(orc, nx, ny, hist, crc):
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    m = info["material"]
+    got = {int(k): int(v) for k, v in zip(*np.unique(m, return_counts=True))}
+    assert got == hist
+    assert zlib.crc32(m.astype("<i4").tobytes()) == crc
+    assert (info["block_iter"] == -1).all() and (info["vy"] == 0).all()
+    assert (info["vx"][m == 3] == np.float32(0.12)).all() and (info["vx"][m != 3] == 0).all()
+
+
+def test_init_known_answer(orc):
+    nx, ny = 64, 40
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    s = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 0, nx * ny))
+    b0, b1 = s.distributions(0), s.distributions(1)
+    fluid = [0.444444, 0.1666665, 0.111111, 0.0555555, 0.111111, 0.0277777, 0.0277777, 0.0277777, 0.0277777]
+    # (50, 20) is bulk fluid: the R=28 preset discs sit at x <= 41 on a 64-wide lattice
+    np.testing.assert_allclose(b0[:, 20, 50], np.array(fluid, np.float32), rtol=0, atol=1e-7)
+    assert b0[1, 20, 50] == np.float32(0.111111) + np.float32(0.111111) * np.float32(0.5)
+    np.testing.assert_array_equal(b1[:, 20, 50], [0, b0[1, 20, 50], 0, b0[3, 20, 50], 0, 0, 0, 0, 0])
+    assert (b0[:, 0, :] == 0).all() and (b1[:, 0, :] == 0).all()  # wall row
+    # lid-driven cavity: no +x bias
+    info = orc.init_lattice_material(nx, ny, W.LID_DRIVEN_CAVITY)
+    s = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 1, nx * ny))
+    assert s.distributions(0)[1, 5, 5] == np.float32(0.111111) and (s.distributions(1)[:, 5, 5] == 0).all()
+
+
+def test_total_mass_known_answers(orc):
+    """M0/M1/M100 of the default 600x375 channel, tau=0.56."""
+    nx, ny = 600, 375
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    s = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 0, nx * ny), threads=orc.lib().orc_get_max_threads())
+    assert round(s.total_mass(), 3) == 216425.742
+    s.step(1)
+    assert round(s.total_mass(), 3) == 216148.638
+    s.step(99)
+    assert round(s.total_mass(), 3) == 216071.546
+
+
+def test_uniform_periodic_cell_hand_computed(orc):
+    """One step of an all-fluid periodic lattice from f=w: rho = sum w (clamped no-op), u = 0,
+    feq_i = rho*w_i*1.0, t = f - omega*(f - feq)."""
+    nx, ny = 8, 6
+    info = np.zeros(nx * ny, W.LATTICE_INFO_DTYPE)
+    info["material"] = W.BULK
+    info["block_iter"] = -1
+    u = orc.uniform_new(tau_default(), 1, nx * ny)
+    s = orc.OracleSim(nx, ny, info, u)
+    s.step(1)
+    w = np.array([u.e_w_max[i][2] for i in range(9)], np.float32)
+    rho = np.float32(0)
+    for i in range(9):
+        rho = np.float32(rho + w[i])
+    om = np.float32(u.omega)
+    for i in range(9):
+        feq = np.float32(np.float32(rho * w[i]) * np.float32(1.0))
+        t = np.float32(w[i] - np.float32(om * np.float32(w[i] - feq)))
+        assert (s.distributions(1)[i] == t).all()
+    m = s.macro()
+    assert (m[0] == 0).all() and (m[1] == 0).all() and (m[2] == rho).all()
+
+
+def test_bounce_back_known_answer(orc):
+    """A fluid cell next to a wall gets its own post-collision f*_i back in inv(i) one step later;
+    the value sits in the solid neighbour's slot and the fluid slot is zeroed (boundary.wgsl:28-31).
+    Ring cells (ghost column) receive nothing from a solid neighbour."""
+    nx, ny = 12, 9
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    u = orc.uniform_new(tau_default(), 1, nx * ny)
+    s = orc.OracleSim(nx, ny, info, u)
+    before = s.distributions(0).copy()
+    s.step(1)
+    after = s.distributions(1)
+    # cell (x=1,y=4) is strictly interior with the wall x=0 to its left: direction 3 (e=(-1,0))
+    x, y = 1, 4
+    assert after[3, y, x] == 0.0                     # own slot zeroed
+    assert after[1, y, x - 1] != 0.0                 # f*_3 parked in wall slot inv(3)=1
+    s.step(1)
+    # the second step pulled direction 1 at (1,4) from the wall slot = its own f*_3
+    prev = s.distributions(1)
+    assert prev[1, y, x - 1] != 0 and before[3, y, x] != 0
+    # first step after init pulled zeros from solids: rho at wall-adjacent cells hit the 0.8 clamp
+    info2 = orc.init_lattice_material(64, 40, W.POISEUILLE)
+    s2 = orc.OracleSim(64, 40, info2, orc.uniform_new(tau_default(), 0, 64 * 40))
+    s2.step(1)
+    assert (s2.macro()[2][1, 2:-2] == np.float32(0.8)).any()
+    # ghost cell (x=0, y=1) neighbours the wall row y=0 but is on the ring: its slots facing the wall keep values
+    d = s2.distributions(1)
+    assert d[2, 1, 0] != 0.0 and d[4, 0, 0] == 0.0          # the ring cell (0,1) parks nothing in the wall above it
+    assert d[4, 0, 50] != 0.0 and d[2, 1, 50] == 0.0        # interior cell (50,1): f*_2 parked in wall slot 4
+
+
+def test_transient_force_cell_flips_after_block_iter(orc):
+    nx, ny = 20, 16
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    u = orc.uniform_new(tau_default(), 1, nx * ny)
+    s = orc.OracleSim(nx, ny, info, u)  # init first (it would disarm block_iter>0 cells)
+    cell = np.zeros(1, W.LATTICE_INFO_DTYPE)
+    cell[0] = (W.EXTERNAL_FORCE, 5, 0.05, -0.02)
+    s.write_lattice_info((nx * 7 + 9) * 16, cell)
+    for k in range(1, 8):
+        s.step(1)
+        c = s.info[nx * 7 + 9]
+        if k < 5:
+            assert (c["material"], c["block_iter"]) == (6, 5 - k)
+        else:
+            assert (c["material"], c["block_iter"]) == (1, 0)
+        assert c["vx"] == np.float32(0.05)  # vx/vy are retained after the flip
+    # init.wgsl disarms armed cells
+    s.write_lattice_info((nx * 7 + 9) * 16, cell)
+    s.reset()
+    c = s.info[nx * 7 + 9]
+    assert (c["material"], c["block_iter"], c["vx"], c["vy"]) == (1, 0, 0.0, 0.0)
+
+
+def test_direction_clamp_trips(orc):
+    """Per-direction clamp [0, max_i] (collide_stream.wgsl:79-83) trips next to a strong force patch."""
+    nx, ny = 24, 20
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    g = info.reshape(ny, nx)
+    g[8:12, 8:12] = (W.EXTERNAL_FORCE, -1, 0.9, 0.9)
+    u = orc.uniform_new(tau_default(), 1, nx * ny)
+    s = orc.OracleSim(nx, ny, info, u)
+    s.step(3)
+    cur = s.distributions(s.swap)
+    mx = np.array([u.e_w_max[i][3] for i in range(9)], np.float32)
+    assert (cur >= 0).all() and all((cur[i] <= mx[i]).all() for i in range(9))
+    assert any((cur[i] == mx[i]).any() for i in range(9)) and (cur[:, 8:12, 8:12] == 0).any()
+
+
+@pytest.mark.parametrize("path", golden_cases())
+def test_oracle_matches_golden(orc, path):
+    g = np.load(path)
+    nx, ny, steps = int(g["nx"]), int(g["ny"]), int(g["steps"])
+    fluid_ty = 1 if int(g["preset"]) == W.LID_DRIVEN_CAVITY else 0
+    s = orc.OracleSim(nx, ny, g["info"], orc.uniform_new(tau_default(), fluid_ty, nx * ny))
+    for off, cell in zip(g["post_offsets"], g["post_cells"]):  # force cells armed after init
+        s.write_lattice_info(int(off), np.array([cell], W.LATTICE_INFO_DTYPE))
+    s.step(steps)
+    assert s.swap == int(g["swap"])
+    assert_bits_equal(s.distributions(s.swap), g["buf_cur"], "current buffer")
+    assert_bits_equal(s.distributions(1 - s.swap), g["buf_prev"], "previous buffer")
+    m = s.macro()
+    assert_bits_equal(m[0], g["ux"], "ux")
+    assert_bits_equal(m[1], g["uy"], "uy")
+    assert_bits_equal(m[2], g["rho"], "rho")
+    np.testing.assert_array_equal(s.info["material"].reshape(ny, nx), g["material"])
+    np.testing.assert_array_equal(s.info["block_iter"].reshape(ny, nx), g["block_iter"])
+
+
+@pytest.mark.parametrize("nx,ny,preset,steps", [(150, 94, W.POISEUILLE, 120), (33, 27, W.LID_DRIVEN_CAVITY, 60),
+                                                (17, 9, W.CUSTOM, 40)])
+def test_oracle_matches_numpy_restatement(orc, nx, ny, preset, steps):
+    info = orc.init_lattice_material(nx, ny, preset)
+    fluid_ty = 1 if preset == W.LID_DRIVEN_CAVITY else 0
+    u = orc.uniform_new(tau_default(), fluid_ty, nx * ny)
+    a = orc.OracleSim(nx, ny, info, u, threads=3)  # OpenMP on: collide pass is order independent
+    b = R.NpSim(nx, ny, info, u)
+    for _ in range(2):
+        a.step(steps // 2)
+        b.step(steps // 2)
+        assert_bits_equal(a.distributions(a.swap), b.buf[b.swap], "current")
+        assert_bits_equal(a.distributions(1 - a.swap), b.buf[1 - b.swap], "previous")
+    assert_bits_equal(a.macro(), np.stack(b.macro), "macro")
+
+
+def test_f16_conversion_matches_numpy(orc):
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([
+        rng.standard_normal(4000).astype(np.float32) * np.float32(0.2),
+        np.array([0.0, -0.0, 1.0, 0.8, 1.2, 65504.0, 65519.9, 65520.0, 1e-8, 6e-8, 2.98e-8, 2.9802322e-8, 6.1e-5, 6.0975e-5,
+                  -0.12, 1e10, np.inf, -np.inf], np.float32),
+        np.float32(2.0) ** rng.integers(-26, 16, 500).astype(np.float32) * (1 + rng.random(500).astype(np.float32)),
+    ])
+    got = orc.f32_to_f16_bits(vals)
+    want = vals.astype(np.float16).view(np.uint16)
+    np.testing.assert_array_equal(got, want)
+    back = np.array([orc.lib().orc_f16_to_f32(int(h)) for h in got[:200]], np.float32)
+    np.testing.assert_array_equal(back.view(np.uint32), want[:200].view(np.float16).astype(np.float32).view(np.uint32))
+
+
+def test_mass_drifts_like_the_reference(orc):
+    """The reference does not conserve mass (truncated weights + clamps): the oracle must
+    show the drift rather than hide it."""
+    nx, ny = 128, 128
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    s = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 1, nx * ny), threads=4)
+    m0 = s.total_mass()
+    s.step(400)
+    drift = (s.total_mass() - m0) / m0
+    assert -5e-2 < drift < -1e-5
