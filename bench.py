@@ -213,31 +213,32 @@ def main():
 
     nx, ny, name = workload_for(args.gpus, args.lattice)
     setting = sb.SettingObj(animation_type=W.POISEUILLE)
-    flags = sb.FLAG_KERNEL_GENERIC if args.generic else 0
     canvas = (nx * 2, ny * 2)
-    if world == 1:
-        node = sb.D2Q9Node(canvas, setting, lattice=(nx, ny), device_preset=W.POISEUILLE, device=local_rank, flags=flags)
-        slab = None
-    else:
-        slab = SlabRank(canvas, setting, lattice=(nx, ny), dist=dist, device=local_rank, device_preset=W.POISEUILLE,
-                        flags=flags)
-        node = slab.node
 
-    def barrier():
-        node.sync()
+    def make_sim(flags):
+        if world == 1:
+            return None, sb.D2Q9Node(canvas, setting, lattice=(nx, ny), device_preset=W.POISEUILLE, device=local_rank,
+                                     flags=flags)
+        sl = SlabRank(canvas, setting, lattice=(nx, ny), dist=dist, device=local_rank, device_preset=W.POISEUILLE,
+                      flags=flags)
+        return sl, sl.node
+
+    def barrier(n):
+        n.sync()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
+    slab, node = make_sim(sb.FLAG_KERNEL_GENERIC if args.generic else 0)
     sampler = ClockSampler(local_rank)
     sampler.start()
     node.step_n(args.warmup)
-    barrier()
+    barrier(node)
     launches0 = node.launch_count
     t0 = time.perf_counter()
     node.step_n(args.steps)          # K launches, CUDA events recorded around them on the library's stream
     ms = node.last_step_n_ms()       # synchronises on the end event
-    barrier()
+    barrier(node)
     t1 = time.perf_counter()
     launches = node.launch_count - launches0
     clocks = sampler.stop(t0, t1)
@@ -248,45 +249,52 @@ def main():
     sites = nx * ny
     value = sites * args.steps / (ms * 1e-3) / 1e6
     mass = slab.total_mass() if slab is not None else node.total_mass()
+    barrier(node)  # no slab may unmap memory a neighbour still reads
+    node.close()
 
-    # ---- e2e through the host API with host buffers (N=1 only: the field read is single-slab)
+    # ---- e2e: the same steps driven through the host API with HOST buffers in the timed region.
+    # The handle is the tracer/renderer configuration (macro texture written by every step, like
+    # collide_stream.wgsl:74); every rank uploads a patch of its slab and reads its slab's field.
     e2e = None
-    if world == 1 and args.e2e_steps > 0:
-        rows = 56
-        patch_t = torch.empty(rows * nx * 16, dtype=torch.uint8).pin_memory()
-        macro_t = torch.empty(sites * 8, dtype=torch.uint8).pin_memory()
-        patch = patch_t.numpy().view(W.LATTICE_INFO_DTYPE)
-        macro = macro_t.numpy()
-        y_lo = ny // 2 - 28
-        full = node.read_lattice_info()
-        patch[:] = full[y_lo * nx:(y_lo + rows) * nx]  # re-upload of unchanged rows: same traffic, same mask
-        del full
-        import ctypes as C
-
+    if args.e2e_steps > 0:
         from simuverse_b200._capi import MACRO_RGBA16F, check, lib
         from simuverse_b200.wire import ptr
 
+        slab2, node2 = make_sim(sb.FLAG_MACRO_EVERY_STEP)
+        rows = min(56, node2.rows)
+        patch_t = torch.empty(rows * nx * 16, dtype=torch.uint8).pin_memory()
+        macro_t = torch.empty(node2.rows * nx * 8, dtype=torch.uint8).pin_memory()
+        patch = patch_t.numpy().view(W.LATTICE_INFO_DTYPE)
+        macro = macro_t.numpy()
+        l_lo = (node2.rows - rows) // 2
+        patch[:] = node2.read_lattice_info()[l_lo * nx:(l_lo + rows) * nx]  # unchanged rows: same mask, real traffic
+        off = (node2.y0 + l_lo) * nx * 16
+
         def e2e_step():
-            check(lib.lbm_write_lattice_info(node._h, y_lo * nx * 16, ptr(patch), patch.nbytes), node._h)
-            check(lib.lbm_step_n(node._h, 1), node._h)
-            check(lib.lbm_read_macro(node._h, MACRO_RGBA16F, ptr(macro)), node._h)
+            check(lib.lbm_write_lattice_info(node2._h, off, ptr(patch), patch.nbytes), node2._h)
+            check(lib.lbm_step_n(node2._h, 1), node2._h)
+            check(lib.lbm_read_macro(node2._h, MACRO_RGBA16F, ptr(macro)), node2._h)
 
         for _ in range(3):
             e2e_step()
-        barrier()
+        barrier(node2)
         ta = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step()
-        barrier()
-        tb = time.perf_counter()
-        e2e = {"value": sites * args.e2e_steps / (tb - ta) / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(patch.nbytes), "d2h_bytes_per_step": int(macro.nbytes),
+        barrier(node2)
+        dt = time.perf_counter() - ta
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": sites * args.e2e_steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(patch.nbytes) * world, "d2h_bytes_per_step": int(macro.nbytes) * world,
                "steps": args.e2e_steps,
-               "what": "per step: lbm_write_lattice_info(56-row patch, pinned host) + lbm_step_n(1) + "
-                       "lbm_read_macro(RGBA16F field -> pinned host), synchronous"}
-        _ = C
-    elif world > 1:
-        e2e = None
+               "what": "per step, per rank: lbm_write_lattice_info(56-row LatticeInfo patch from pinned host memory) + "
+                       "lbm_step_n(1) (macro texture written by the step) + lbm_read_macro(RGBA16F field of the slab "
+                       "-> pinned host memory); synchronous calls, wall clock, max over ranks"}
+        barrier(node2)
+        node2.close()
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
@@ -312,8 +320,6 @@ def main():
         if world == 1 and args.cpu_seconds > 0:
             out["cpu_baseline"] = cpu_leg(nx, ny, args.cpu_seconds)
         print(json.dumps(out))
-    barrier()  # no slab may unmap memory a neighbour still reads
-    node.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

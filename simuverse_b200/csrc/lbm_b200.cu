@@ -53,6 +53,8 @@ struct LbmSim {
     size_t flag_off = 0;
     double *d_mass = nullptr;
     float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
+    __half *scratch16 = nullptr; // RGBA16F texels for the on-demand macro read
+    uint64_t steps_since_reset = 0;
     bool have_uniform = false;
     bool have_info = false;
     LbmUniform u{};
@@ -130,6 +132,19 @@ int ensure_scratch32(LbmSim *s) {
     return LBM_OK;
 }
 
+int ensure_scratch16(LbmSim *s) {
+    if (s->scratch16) return LBM_OK;
+    CU(cudaMalloc(&s->scratch16, sizeof(__half) * 4 * (size_t)s->P.h * s->P.nx));
+    return LBM_OK;
+}
+
+// init.wgsl:62 leaves the macro texture at (0,0,0,1) everywhere
+__global__ void k_macro_after_init(const __grid_constant__ SlabParams P) {
+    const size_t n = (size_t)P.h * P.nx;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x)
+        store_macro(P, (int)(c % P.nx), (int)(c / P.nx), 0.0f, 0.0f, 0.0f, 1.0f);
+}
+
 int launch_step(LbmSim *s, int rb) {
     int rc = LBM_OK;
     if (s->d.flags & LBM_FLAG_KERNEL_GENERIC) {
@@ -151,6 +166,7 @@ int launch_step(LbmSim *s, int rb) {
         s->launches++;
     }
     s->sync.step_no++;
+    s->steps_since_reset++;
     return LBM_OK;
 }
 
@@ -200,6 +216,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->P.info);
     cudaFree(s->P.macro16);
     cudaFree(s->scratch32);
+    cudaFree(s->scratch16);
     cudaFree(s->d_mass);
     cudaFree(s->particles);
     cudaFree(s->canvas);
@@ -397,6 +414,7 @@ extern "C" int lbm_reset(LbmSim *s) {
     int rc = check_launch(s, "k_init");
     if (rc) return rc;
     s->swap = 0;
+    s->steps_since_reset = 0;
     // init.wgsl:51-59 may have turned armed force cells back into bulk
     return derive_rows(s, 0, s->P.h);
 }
@@ -488,29 +506,32 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
     int rc = ready_to_step(s);
     if (rc) return rc;
     SlabParams Q = P;
-    __half *tmp16 = nullptr;
     if (format == LBM_MACRO_F32_PLANES) {
         rc = ensure_scratch32(s);
         if (rc) return rc;
         Q.macro32 = s->scratch32;
         Q.macro16 = nullptr;
     } else {
-        CU(cudaMalloc(&tmp16, sizeof(__half) * 4 * n));
-        Q.macro16 = tmp16;
+        rc = ensure_scratch16(s);
+        if (rc) return rc;
+        Q.macro16 = s->scratch16;
         Q.macro32 = nullptr;
     }
-    dim3 block(64, 4);
-    k_step_generic<1><<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(Q, s->swap ^ 1, 0, P.h);
-    rc = check_launch(s, "k_step_generic<macro>");
-    if (rc == LBM_OK) {
-        cudaError_t e = (format == LBM_MACRO_F32_PLANES)
-                            ? cudaMemcpyAsync(dst, Q.macro32, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream)
-                            : cudaMemcpyAsync(dst, tmp16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-        if (e != cudaSuccess) rc = fail(s, LBM_ERR_CUDA, "macro read-back failed: %s", cudaGetErrorString(e));
+    if (s->steps_since_reset == 0) {
+        k_macro_after_init<<<148 * 8, 256, 0, s->stream>>>(Q);
+        rc = check_launch(s, "k_macro_after_init");
+    } else {
+        dim3 block(64, 4);
+        k_step_generic<1><<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(Q, s->swap ^ 1, 0, P.h);
+        rc = check_launch(s, "k_step_generic<macro>");
     }
-    if (tmp16) cudaFree(tmp16);
-    return rc;
+    if (rc) return rc;
+    if (format == LBM_MACRO_F32_PLANES)
+        CU(cudaMemcpyAsync(dst, Q.macro32, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
+    else
+        CU(cudaMemcpyAsync(dst, Q.macro16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
 }
 
 extern "C" int lbm_read_lattice_info(LbmSim *s, LatticeInfo *dst) {
