@@ -27,6 +27,41 @@ def neighbours(rank, world):
     return (rank - 1) % world, (rank + 1) % world
 
 
+def exchange_blobs(dist, mine, group=None, device=None):
+    """all_gather of one fixed-size byte blob per rank; returns (all blobs, up blob, down blob).
+    Works on any backend (gloo on CPU tensors, nccl on CUDA tensors)."""
+    import torch
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if device is None:
+        backend = dist.get_backend(group)
+        device = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+    blobs = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(blobs, t, group=group)
+    out = [bytes(b.cpu().numpy()) for b in blobs]
+    up, down = neighbours(rank, world)
+    return out, out[up], out[down]
+
+
+def gather_rows(dist, local, ny, group=None):
+    """Assemble per-slab arrays of shape (..., rows_r, nx) into the global (..., ny, nx) on every rank
+    (read-back path of a distributed run; off the hot path)."""
+    import torch
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rows = [slab_bounds(ny, r, world)[1] - slab_bounds(ny, r, world)[0] for r in range(world)]
+    assert local.shape[-2] == rows[rank]
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    pad_shape = local.shape[:-2] + (max(rows), local.shape[-1])
+    pad = torch.zeros(pad_shape, dtype=torch.from_numpy(local[..., :0, :]).dtype, device=dev)
+    pad[..., :rows[rank], :] = torch.from_numpy(np.ascontiguousarray(local)).to(dev)
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return np.concatenate([parts[r][..., :rows[r], :].cpu().numpy() for r in range(world)], axis=-2)
+
+
 class SlabRank:
     """This process' slab of a lattice decomposed over ``dist.get_world_size()`` ranks."""
 
@@ -45,16 +80,13 @@ class SlabRank:
         self.barrier()
 
     def _attach(self):
-        import torch
+        _, up, down = exchange_blobs(self.dist, self.node.ipc_export(), self.group)
+        self.node.ipc_attach(up, down)
 
-        mine = torch.frombuffer(bytearray(self.node.ipc_export()), dtype=torch.uint8)
-        backend = self.dist.get_backend(self.group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        mine = mine.to(dev)
-        blobs = [torch.empty_like(mine) for _ in range(self.world)]
-        self.dist.all_gather(blobs, mine, group=self.group)
-        up, down = neighbours(self.rank, self.world)
-        self.node.ipc_attach(bytes(blobs[up].cpu().numpy()), bytes(blobs[down].cpu().numpy()))
+    def gather_distributions(self, which=None):
+        """Global (9, ny, nx) distributions on every rank."""
+        which = self.node.swap_index if which is None else which
+        return gather_rows(self.dist, self.node.read_distributions(which), self.node.lattice[1], self.group)
 
     def barrier(self):
         """Host-level rendezvous: every slab's queued work is done on return."""

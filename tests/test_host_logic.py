@@ -157,3 +157,17 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".sh")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"
+
+
+def test_cpp_host_mirror_compiles_and_runs(tmp_path):
+    """include/d2q9_node.hpp (C++ mirror of D2Q9Node / FluidSimulator) builds against the library;
+    on a CPU box it must report the missing GPU instead of computing anything."""
+    import subprocess
+
+    exe = tmp_path / "host_mirror_check"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "host_mirror_check.cpp"), sb.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(sb.LIB_PATH), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "HOST_MIRROR_OK" in r.stdout, r.stdout + r.stderr
