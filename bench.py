@@ -43,17 +43,28 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def workload_for(n_gpus, override):
+def workload_for(n_gpus, override, config=None):
+    """(nx, ny, name, kind) of the BASELINE.json config being run. kind: 'steps' or 'frames'."""
+    if config is None:
+        config = 2 if n_gpus == 1 else 3
     if override:
         nx, ny = override
-        name = f"D2Q9 BGK {nx}x{ny} channel + cylinder obstacles (Poiseuille preset), f32"
-    elif n_gpus == 1:
-        nx = ny = 4096
-        name = "D2Q9 BGK 4096x4096 channel + cylinder obstacle, f32, single B200 (BASELINE configs[1])"
-    else:
-        nx = ny = 16384
-        name = f"D2Q9 16384x16384 strong scaling, {n_gpus} y-slabs with peer-memory edge rows (BASELINE configs[2])"
-    return nx, ny, name
+        return nx, ny, f"D2Q9 BGK {nx}x{ny} channel + cylinder obstacles (Poiseuille preset), f32", "steps", config
+    if config == 1:
+        return 600, 375, ("simuverse default lattice 600x375, channel flow past 3 cylinders, 127x80 tracer particles, "
+                          "frame loop of FluidSimulator::compute (BASELINE configs[0])"), "frames", config
+    if config == 2:
+        return 4096, 4096, "D2Q9 BGK 4096x4096 channel + cylinder obstacle, f32, single B200 (BASELINE configs[1])", "steps", config
+    if config == 3:
+        return 16384, 16384, (f"D2Q9 16384x16384 strong scaling, {n_gpus} y-slab(s) with peer-memory edge rows "
+                              "(BASELINE configs[2])"), "steps", config
+    if config == 4:
+        return 16384, 16384 * n_gpus, (f"D2Q9 weak scaling, 16384x16384 per GPU, {n_gpus} y-slab(s) = 16384x{16384 * n_gpus} "
+                                       "(BASELINE configs[3])"), "steps", config
+    if config == 5:
+        return 8192, 8192, ("D2Q9 8192x8192 porous-media mask (30% solid) + 1000x1000 tracer particles updated after "
+                            "every step (BASELINE configs[4])"), "frames", config
+    raise SystemExit(f"unknown --config {config}")
 
 
 class ClockSampler:
@@ -109,14 +120,14 @@ class ClockSampler:
                 "samples": len(win)}
 
 
-def cpu_leg(nx, ny, budget_s, min_steps=3):
+def cpu_leg(nx, ny, budget_s, porous=False, min_steps=3):
     """Times the CPU oracle (OpenMP, all host cores) on rows of the same workload. Returns a dict."""
     import numpy as np
 
     import oracle as orc
 
     cores = orc.lib().orc_get_max_threads()
-    info = orc.init_lattice_material(nx, ny, 4)
+    info = orc.init_porous_material(nx, ny) if porous else orc.init_lattice_material(nx, ny, 4)
     tau = float(np.float32(3.0) * np.float32(0.02) + np.float32(0.5))
     sim = orc.OracleSim(nx, ny, info, orc.uniform_new(tau, 0, (nx * ny) & 0x7FFFFFFF), threads=cores)
     sim.step(1)
@@ -140,12 +151,13 @@ def run_reference(args, rank, world):
 
     import oracle as orc
 
-    nx, ny, name = workload_for(args.gpus, args.lattice)
+    nx, ny, name, _, _ = workload_for(args.gpus, args.lattice, args.config)
     cores = orc.lib().orc_get_max_threads()
     tau = float(np.float32(3.0) * np.float32(0.02) + np.float32(0.5))
     # calibrate on a thin band, then size the band for ~150 s total
     rows = 64
-    info = orc.init_lattice_material(nx, rows, 4)
+    make_info = (lambda r: orc.init_porous_material(nx, r)) if args.config == 5 else (lambda r: orc.init_lattice_material(nx, r, 4))
+    info = make_info(rows)
     sim = orc.OracleSim(nx, rows, info, orc.uniform_new(tau, 0, nx * rows), threads=cores)
     sim.step(1)
     t0 = time.perf_counter()
@@ -153,7 +165,7 @@ def run_reference(args, rank, world):
     per_row = (time.perf_counter() - t0) / 3 / rows
     total = args.steps + args.warmup
     rows = int(max(64, min(ny, 150.0 / total / per_row)))
-    info = orc.init_lattice_material(nx, rows, 4)
+    info = make_info(rows)
     sim = orc.OracleSim(nx, rows, info, orc.uniform_new(tau, 0, nx * rows), threads=cores)
     sim.step(args.warmup)
     t0 = time.perf_counter()
@@ -164,8 +176,8 @@ def run_reference(args, rank, world):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": name, "sample": sample},
+        "scaling": "weak" if (args.gpus == 1 or args.config == 4) else "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": name, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -177,6 +189,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=None, help="BASELINE.json config 1..5 (default 2 at N=1, 3 at N>1)")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of CUDA graphs")
     ap.add_argument("--lattice", type=int, nargs=2, default=None, metavar=("NX", "NY"), help="override the workload")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg (0 = skip)")
@@ -211,17 +225,26 @@ def main():
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nx, ny, name = workload_for(args.gpus, args.lattice)
-    setting = sb.SettingObj(animation_type=W.POISEUILLE)
+    nx, ny, name, kind, config = workload_for(args.gpus, args.lattice, args.config)
+    if kind == "frames" and world > 1:
+        raise SystemExit("configs 1 and 5 (tracer particles) are single-GPU")
+    porous = config == 5
+    setting = sb.SettingObj(animation_type=W.POISEUILLE, particles_count=1000000 if porous else 10000)
     canvas = (nx * 2, ny * 2)
+    preset = sb.PRESET_POROUS if porous else W.POISEUILLE
+    base_flags = (sb.FLAG_KERNEL_GENERIC if args.generic else 0) | (sb.FLAG_NO_GRAPH if args.no_graph else 0)
 
     def make_sim(flags):
+        """(slab or None, node, FluidSimulator or None)"""
+        if kind == "frames":
+            fs = sb.FluidSimulator(canvas, setting, particles=True, lattice=(nx, ny), device_preset=preset,
+                                   device=local_rank, flags=flags)
+            return None, fs.fluid_compute_node, fs
         if world == 1:
-            return None, sb.D2Q9Node(canvas, setting, lattice=(nx, ny), device_preset=W.POISEUILLE, device=local_rank,
-                                     flags=flags)
-        sl = SlabRank(canvas, setting, lattice=(nx, ny), dist=dist, device=local_rank, device_preset=W.POISEUILLE,
-                      flags=flags)
-        return sl, sl.node
+            return None, sb.D2Q9Node(canvas, setting, lattice=(nx, ny), device_preset=preset, device=local_rank,
+                                     flags=flags), None
+        sl = SlabRank(canvas, setting, lattice=(nx, ny), dist=dist, device=local_rank, device_preset=preset, flags=flags)
+        return sl, sl.node, None
 
     def barrier(n):
         n.sync()
@@ -229,14 +252,21 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    slab, node = make_sim(sb.FLAG_KERNEL_GENERIC if args.generic else 0)
+    def advance(n, steps):
+        if kind == "frames":
+            n.compute_frames(steps // 2)   # one frame = 2 lattice updates + 2 particle updates
+        else:
+            n.step_n(steps)
+
+    steps = args.steps - (args.steps % 2) if kind == "frames" else args.steps
+    slab, node, fs = make_sim(base_flags)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    node.step_n(args.warmup)
+    advance(node, args.warmup + (args.warmup % 2))
     barrier(node)
     launches0 = node.launch_count
     t0 = time.perf_counter()
-    node.step_n(args.steps)          # K launches, CUDA events recorded around them on the library's stream
+    advance(node, steps)             # CUDA events recorded around the launches on the library's stream
     ms = node.last_step_n_ms()       # synchronises on the end event
     barrier(node)
     t1 = time.perf_counter()
@@ -247,12 +277,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     sites = nx * ny
-    value = sites * args.steps / (ms * 1e-3) / 1e6
+    value = sites * steps / (ms * 1e-3) / 1e6
     mass = slab.total_mass() if slab is not None else node.total_mass()
     barrier(node)  # no slab may unmap memory a neighbour still reads
     node.close()
 
-    # ---- e2e: the same steps driven through the host API with HOST buffers in the timed region.
+    # ---- e2e: the same updates driven through the host API with HOST buffers in the timed region.
     # The handle is the tracer/renderer configuration (macro texture written by every step, like
     # collide_stream.wgsl:74); every rank uploads a patch of its slab and reads its slab's field.
     e2e = None
@@ -260,7 +290,7 @@ def main():
         from simuverse_b200._capi import MACRO_RGBA16F, check, lib
         from simuverse_b200.wire import ptr
 
-        slab2, node2 = make_sim(sb.FLAG_MACRO_EVERY_STEP)
+        slab2, node2, fs2 = make_sim(base_flags | sb.FLAG_MACRO_EVERY_STEP)
         rows = min(56, node2.rows)
         patch_t = torch.empty(rows * nx * 16, dtype=torch.uint8).pin_memory()
         macro_t = torch.empty(node2.rows * nx * 8, dtype=torch.uint8).pin_memory()
@@ -269,10 +299,18 @@ def main():
         l_lo = (node2.rows - rows) // 2
         patch[:] = node2.read_lattice_info()[l_lo * nx:(l_lo + rows) * nx]  # unchanged rows: same mask, real traffic
         off = (node2.y0 + l_lo) * nx * 16
+        per_call = 2 if kind == "frames" else 1
+        n_part = fs2.particles_num[0] * fs2.particles_num[1] if fs2 is not None else 0
+        parts_t = torch.empty(max(n_part, 1) * 24, dtype=torch.uint8).pin_memory()
+        parts = parts_t.numpy()
 
         def e2e_step():
             check(lib.lbm_write_lattice_info(node2._h, off, ptr(patch), patch.nbytes), node2._h)
-            check(lib.lbm_step_n(node2._h, 1), node2._h)
+            if kind == "frames":
+                check(lib.lbm_compute_frames(node2._h, 1), node2._h)
+                check(lib.lbm_particles_read(node2._h, ptr(parts), n_part), node2._h)
+            else:
+                check(lib.lbm_step_n(node2._h, 1), node2._h)
             check(lib.lbm_read_macro(node2._h, MACRO_RGBA16F, ptr(macro)), node2._h)
 
         for _ in range(3):
@@ -287,24 +325,29 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": sites * args.e2e_steps / dt / 1e6, "unit": "MLUPS",
-               "h2d_bytes_per_step": int(patch.nbytes) * world, "d2h_bytes_per_step": int(macro.nbytes) * world,
-               "steps": args.e2e_steps,
-               "what": "per step, per rank: lbm_write_lattice_info(56-row LatticeInfo patch from pinned host memory) + "
-                       "lbm_step_n(1) (macro texture written by the step) + lbm_read_macro(RGBA16F field of the slab "
-                       "-> pinned host memory); synchronous calls, wall clock, max over ranks"}
+        e2e = {"value": sites * per_call * args.e2e_steps / dt / 1e6, "unit": "MLUPS",
+               "h2d_bytes_per_step": int(patch.nbytes) * world // per_call,
+               "d2h_bytes_per_step": (int(macro.nbytes) + (n_part * 24 if kind == "frames" else 0)) * world // per_call,
+               "steps": args.e2e_steps * per_call,
+               "what": ("per host call, per rank: lbm_write_lattice_info(56-row LatticeInfo patch from pinned host memory) + "
+                        + ("lbm_compute_frames(1) [2 updates + 2 particle updates] + lbm_particles_read + "
+                           if kind == "frames" else "lbm_step_n(1) (macro texture written by the step) + ")
+                        + "lbm_read_macro(RGBA16F field of the slab -> pinned host memory); synchronous calls, "
+                          "wall clock, max over ranks")}
         barrier(node2)
         node2.close()
 
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
-        per_launch_s = ms * 1e-3 / args.steps
+        per_launch_s = ms * 1e-3 / steps      # one k_step_vec launch per lattice update
         achieved = BYTES_PER_SITE * (sites / world) / per_launch_s / 1e9
         out = {
-            "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "lattice": [nx, ny], "tau": 0.56, "l2": "inputs_larger_than_l2",
+            "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak" if (world == 1 or config == 4) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "baseline_config": config, "lattice": [nx, ny], "tau": 0.56,
+                       "l2": "inputs_larger_than_l2" if sites * 72 / world > 2.6e8 else "lattice fits in L2 (the reference's own size)",
+                       "cuda_graphs": not args.no_graph and world == 1,
                        "kernel": "k_step_generic" if args.generic else "k_step_vec", "state": "A/B ping-pong SoA planes",
                        "total_mass_after": mass},
             "clocks": clocks,
@@ -313,12 +356,12 @@ def main():
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_SITE * sites // world,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
-            "host_wall_ms_per_step": (t1 - t0) * 1e3 / args.steps,
+            "host_wall_ms_per_step": (t1 - t0) * 1e3 / steps,
         }
         if e2e is not None:
             out["e2e"] = e2e
         if world == 1 and args.cpu_seconds > 0:
-            out["cpu_baseline"] = cpu_leg(nx, ny, args.cpu_seconds)
+            out["cpu_baseline"] = cpu_leg(nx, ny, args.cpu_seconds, porous)
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()

@@ -19,6 +19,7 @@
  *   lbm_step                   compute_by_pass(cpass, swap_index)        d2q9_node.rs:302-312
  *                              = collide_stream.wgsl:25-88 then boundary.wgsl:3-35, fused
  *   lbm_step_n                 the frame loop's alternation 0,1,0,1,...  fluid_simulator.rs:223-231
+ *   lbm_compute_frames         FluidSimulator::compute, n times          fluid_simulator.rs:217-232
  *   lbm_read_macro             macro_tex (RGBA16F) contents              d2q9_node.rs:91-104
  *   lbm_particles_update       particle_update_node.compute_by_pass      fluid_simulator.rs:225,229
  *                              = particle_update.wgsl:55-88
@@ -67,6 +68,8 @@ typedef enum LbmStatus {
                                           collide_stream.wgsl:74 (needed by the tracer particles).
                                           Off: the field is produced on demand by lbm_read_macro. */
 #define LBM_FLAG_KERNEL_GENERIC   0x2u /* force the one-thread-per-cell kernel (A/B testing) */
+#define LBM_FLAG_NO_GRAPH         0x4u /* launch every kernel individually instead of replaying CUDA
+                                          graphs of 16 steps / one frame (A/B testing) */
 
 /* lbm_read_macro formats */
 #define LBM_MACRO_F32_PLANES 0 /* 3 planes (u.x, u.y, rho) of rows*nx f32, before the f16 store */
@@ -115,6 +118,9 @@ int lbm_generate_lattice_info(LbmSim *sim, int32_t kind, uint64_t seed, float so
 int lbm_reset(LbmSim *sim);                         /* init.wgsl; next step reads buffer 0 */
 int lbm_step(LbmSim *sim, int32_t swap_index);      /* reads buffer swap_index, writes the other */
 int lbm_step_n(LbmSim *sim, int32_t n);             /* n steps alternating from lbm_swap_index */
+/* n_frames times FluidSimulator::compute (fluid_simulator.rs:217-232): step(0), particle update,
+ * step(1), particle update (the particle updates only if the handle has tracer particles). */
+int lbm_compute_frames(LbmSim *sim, int32_t n_frames);
 int lbm_swap_index(const LbmSim *sim);              /* buffer the next lbm_step_n step reads */
 int lbm_sync(LbmSim *sim);
 

@@ -99,6 +99,7 @@ pub struct Pixel {
 pub const LBM_OK: c_int = 0;
 pub const LBM_FLAG_MACRO_EVERY_STEP: u32 = 0x1;
 pub const LBM_FLAG_KERNEL_GENERIC: u32 = 0x2;
+pub const LBM_FLAG_NO_GRAPH: u32 = 0x4;
 pub const LBM_MACRO_F32_PLANES: i32 = 0;
 pub const LBM_MACRO_RGBA16F: i32 = 1;
 
@@ -118,6 +119,7 @@ unsafe extern "C" {
     pub fn lbm_reset(sim: *mut LbmSim) -> c_int;
     pub fn lbm_step(sim: *mut LbmSim, swap_index: i32) -> c_int;
     pub fn lbm_step_n(sim: *mut LbmSim, n: i32) -> c_int;
+    pub fn lbm_compute_frames(sim: *mut LbmSim, n_frames: i32) -> c_int;
     pub fn lbm_swap_index(sim: *const LbmSim) -> c_int;
     pub fn lbm_sync(sim: *mut LbmSim) -> c_int;
 

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "_native", "liblbm_b200.so")
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_STATE = range(7)
 FLAG_MACRO_EVERY_STEP = 0x1
 FLAG_KERNEL_GENERIC = 0x2
+FLAG_NO_GRAPH = 0x4
 MACRO_F32_PLANES, MACRO_RGBA16F = 0, 1
 PRESET_POROUS = 100
 
@@ -63,6 +64,7 @@ PROTOTYPES = {
     "lbm_reset": (C.c_int, [_H]),
     "lbm_step": (C.c_int, [_H, _i32]),
     "lbm_step_n": (C.c_int, [_H, _i32]),
+    "lbm_compute_frames": (C.c_int, [_H, _i32]),
     "lbm_swap_index": (C.c_int, [_H]),
     "lbm_sync": (C.c_int, [_H]),
     "lbm_slab_rows": (C.c_int, [_H, C.POINTER(_i32), C.POINTER(_i32)]),

@@ -72,6 +72,10 @@ struct LbmSim {
     bool peer_ipc[2] = {false, false};
     StepSync sync{};
     bool attached = false;
+    // CUDA graphs of kGraphSteps consecutive steps / one frame (single-slab handles only): removes the
+    // per-launch host cost and most of the inter-kernel gap; rebuilt whenever a kernel parameter changes
+    cudaGraphExec_t graph_steps[2] = {nullptr, nullptr}; // indexed by the swap index of the first step
+    cudaGraphExec_t graph_frame = nullptr;
     std::string err;
 };
 
@@ -177,6 +181,43 @@ int ready_to_step(LbmSim *s) {
     return LBM_OK;
 }
 
+constexpr int kGraphSteps = 16;
+
+void invalidate_graphs(LbmSim *s) {
+    for (auto &g : s->graph_steps)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (s->graph_frame) { cudaGraphExecDestroy(s->graph_frame); s->graph_frame = nullptr; }
+}
+
+bool graphs_enabled(const LbmSim *s) { return s->d.world == 1 && !(s->d.flags & LBM_FLAG_NO_GRAPH); }
+
+int launch_particles(LbmSim *s) {
+    cudaError_t e = launch_particle_update(s->P, s->field, s->pu, s->particles, s->canvas, s->stream);
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_particle_update failed: %s", cudaGetErrorString(e));
+    s->launches++;
+    return LBM_OK;
+}
+
+// Captures `body` (kernel launches on s->stream) into an executable graph.
+template <typename F>
+int capture_graph(LbmSim *s, cudaGraphExec_t *out, F body) {
+    const uint64_t launches = s->launches, since = s->steps_since_reset;
+    const unsigned int step_no = s->sync.step_no;
+    CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = body();
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    s->launches = launches; // nothing ran yet
+    s->steps_since_reset = since;
+    s->sync.step_no = step_no;
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return LBM_OK;
+}
+
 }  // namespace
 
 // =================================================================== lifecycle
@@ -208,6 +249,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    invalidate_graphs(s);
     for (int k = 0; k < 2; k++)
         if (s->peer_ipc[k] && s->peer_base[k]) cudaIpcCloseMemHandle(s->peer_base[k]);
     cudaFree(s->arena);
@@ -337,6 +379,7 @@ extern "C" int lbm_write_uniform(LbmSim *s, const LbmUniform *u) {
         s->P.k.mx[i] = u->e_w_max[i][3];
     }
     s->have_uniform = true;
+    invalidate_graphs(s);
     return LBM_OK;
 }
 
@@ -346,6 +389,7 @@ extern "C" int lbm_write_field_uniform(LbmSim *s, const FieldUniform *f) {
         return fail(s, LBM_ERR_INVALID_ARG, "FieldUniform.lattice_size %dx%d does not match the handle's %dx%d",
                     f->lattice_size[0], f->lattice_size[1], s->d.nx, s->d.ny);
     s->field = *f;
+    invalidate_graphs(s);
     return LBM_OK;
 }
 
@@ -436,12 +480,77 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
     int rc = ready_to_step(s);
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
+    int left = n;
+    if (graphs_enabled(s) && n >= 2 * kGraphSteps) {
+        cudaGraphExec_t &g = s->graph_steps[s->swap];
+        if (!g) {
+            const int first = s->swap;
+            rc = capture_graph(s, &g, [&]() {
+                int r = LBM_OK;
+                for (int i = 0; i < kGraphSteps && r == LBM_OK; i++) r = launch_step(s, first ^ (i & 1));
+                return r;
+            });
+            if (rc) return rc;
+        }
+    }
     CU(cudaEventRecord(s->ev0, s->stream));
-    for (int i = 0; i < n; i++) {
+    if (graphs_enabled(s) && n >= 2 * kGraphSteps) {
+        cudaGraphExec_t g = s->graph_steps[s->swap];
+        for (; left >= kGraphSteps; left -= kGraphSteps) { // an even number of steps: swap index unchanged
+            CU(cudaGraphLaunch(g, s->stream));
+            s->launches += kGraphSteps;
+            s->steps_since_reset += kGraphSteps;
+            s->sync.step_no += kGraphSteps;
+        }
+    }
+    for (int i = 0; i < left; i++) {
         rc = launch_step(s, s->swap);
         if (rc) return rc;
         s->swap ^= 1;
     }
+    CU(cudaEventRecord(s->ev1, s->stream));
+    s->timed = true;
+    return LBM_OK;
+}
+
+// FluidSimulator::compute (fluid_simulator.rs:217-232) n_frames times:
+// step(0), particle update, step(1), particle update.
+extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
+    if (!s || n_frames < 0) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    int rc = ready_to_step(s);
+    if (rc) return rc;
+    const bool with_particles = s->particles != nullptr;
+    if (with_particles) {
+        if (!s->have_pu) return fail(s, LBM_ERR_STATE, "lbm_write_particle_uniform has not been called");
+        if (!s->P.macro16) return fail(s, LBM_ERR_STATE, "tracer particles need LBM_FLAG_MACRO_EVERY_STEP");
+    }
+    CU(cudaSetDevice(s->device));
+    auto frame = [&]() {
+        int r = launch_step(s, 0);
+        if (r == LBM_OK && with_particles) r = launch_particles(s);
+        if (r == LBM_OK) r = launch_step(s, 1);
+        if (r == LBM_OK && with_particles) r = launch_particles(s);
+        return r;
+    };
+    const bool use_graph = graphs_enabled(s) && n_frames >= 4;
+    if (use_graph && !s->graph_frame) {
+        rc = capture_graph(s, &s->graph_frame, frame);
+        if (rc) return rc;
+    }
+    const uint64_t per_frame = with_particles ? 4 : 2;
+    CU(cudaEventRecord(s->ev0, s->stream));
+    for (int f = 0; f < n_frames; f++) {
+        if (use_graph) {
+            CU(cudaGraphLaunch(s->graph_frame, s->stream));
+            s->launches += per_frame;
+            s->steps_since_reset += 2;
+            s->sync.step_no += 2;
+        } else {
+            rc = frame();
+            if (rc) return rc;
+        }
+    }
+    if (n_frames > 0) s->swap = 0; // a frame ends with step(1): the next step reads buffer 0
     CU(cudaEventRecord(s->ev1, s->stream));
     s->timed = true;
     return LBM_OK;
@@ -563,6 +672,7 @@ extern "C" int lbm_write_particle_uniform(LbmSim *s, const ParticleUniform *pu) 
         return fail(s, LBM_ERR_INVALID_ARG, "particle grid %dx%d exceeds max_particles=%d", pu->num[0], pu->num[1], s->d.max_particles);
     s->pu = *pu;
     s->have_pu = true;
+    invalidate_graphs(s);
     return LBM_OK;
 }
 
@@ -582,10 +692,7 @@ extern "C" int lbm_particles_update(LbmSim *s) {
     if (!s->have_pu) return fail(s, LBM_ERR_STATE, "lbm_write_particle_uniform has not been called");
     if (!s->P.macro16) return fail(s, LBM_ERR_STATE, "tracer particles read the macro texture: create the handle with LBM_FLAG_MACRO_EVERY_STEP");
     CU(cudaSetDevice(s->device));
-    cudaError_t e = launch_particle_update(s->P, s->field, s->pu, s->particles, s->canvas, s->stream);
-    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_particle_update failed: %s", cudaGetErrorString(e));
-    s->launches++;
-    return LBM_OK;
+    return launch_particles(s);
 }
 
 extern "C" int lbm_particles_read(LbmSim *s, TrajectoryParticle *dst, uint64_t count) {

@@ -206,6 +206,10 @@ class D2Q9Node:
     def step_n(self, n):
         check(lib.lbm_step_n(self._h, n), self._h)
 
+    def compute_frames(self, n_frames):
+        """``FluidSimulator::compute`` n times inside the library (fluid_simulator.rs:217-232)."""
+        check(lib.lbm_compute_frames(self._h, n_frames), self._h)
+
     @property
     def swap_index(self):
         return lib.lbm_swap_index(self._h)

@@ -98,12 +98,6 @@ class FluidSimulator:
         self.fluid_compute_node.reset_lattice_info()
         self.pre_pos = (0.0, 0.0)
 
-    def compute(self):
+    def compute(self, n_frames=1):
         """fluid_simulator.rs:217-232: one frame = step(0), particles, step(1), particles."""
-        node = self.fluid_compute_node
-        node.compute_by_pass(0)
-        if self._particles:
-            node.particles_update()
-        node.compute_by_pass(1)
-        if self._particles:
-            node.particles_update()
+        self.fluid_compute_node.compute_frames(n_frames)
