@@ -71,6 +71,7 @@ struct LbmSim {
     void *peer_base[2] = {nullptr, nullptr}; // IPC-opened arenas (up, down); nullptr when same-process
     bool peer_ipc[2] = {false, false};
     StepSync sync{};
+    MixedList mixed{};
     bool attached = false;
     // CUDA graphs of kGraphSteps consecutive steps / one frame (single-slab handles only): removes the
     // per-launch host cost and most of the inter-kernel gap; rebuilt whenever a kernel parameter changes
@@ -110,13 +111,29 @@ int check_launch(LbmSim *s, const char *what) {
 
 dim3 grid2d(int nx, int rows, dim3 block) { return dim3((nx + block.x - 1) / block.x, (rows + block.y - 1) / block.y, 1); }
 
+void invalidate_graphs(LbmSim *s);
+
 int derive_rows(LbmSim *s, int l0, int l1) {
     l0 = std::max(l0, 0);
     l1 = std::min(l1, s->P.h);
     if (l0 >= l1) return LBM_OK;
     dim3 block(64, 4);
     k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1);
-    return check_launch(s, "k_derive");
+    int rc = check_launch(s, "k_derive");
+    if (rc) return rc;
+    // the mask changed: rebuild the list of warps k_step_vec leaves to k_step_mixed
+    MixedList &M = s->mixed;
+    if (M.total > 0) {
+        CU(cudaMemsetAsync(M.count_dev, 0, sizeof(uint32_t), s->stream));
+        k_scan_mixed<<<(M.total + 255) / 256, 256, 0, s->stream>>>(s->P, M.list, M.count_dev, M.warps_per_row);
+        if ((rc = check_launch(s, "k_scan_mixed"))) return rc;
+        CU(cudaMemcpyAsync(&M.count, M.count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        M.everywhere = M.count > M.total / 2;
+        M.rare = M.count <= M.total / 8;
+    }
+    invalidate_graphs(s); // launch geometry is baked into captured graphs
+    return LBM_OK;
 }
 
 bool uniform_is_d2q9(const LbmUniform *u) {
@@ -165,9 +182,10 @@ int launch_step(LbmSim *s, int rb) {
             if ((rc = check_launch(s, "k_signal"))) return rc;
         }
     } else {
-        cudaError_t e = launch_step_vec(s->P, s->sync, rb, s->stream);
-        if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_step_vec failed: %s", cudaGetErrorString(e));
-        s->launches++;
+        int n = 0;
+        cudaError_t e = launch_step_vec(s->P, s->sync, s->mixed, rb, s->stream, &n);
+        if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_step_vec / k_step_mixed failed: %s", cudaGetErrorString(e));
+        s->launches += n;
     }
     s->sync.step_no++;
     s->steps_since_reset++;
@@ -260,6 +278,8 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->scratch32);
     cudaFree(s->scratch16);
     cudaFree(s->d_mass);
+    cudaFree(s->mixed.list);
+    cudaFree(s->mixed.count_dev);
     cudaFree(s->particles);
     cudaFree(s->canvas);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -330,6 +350,12 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
         CU(cudaMemsetAsync(P.macro16, 0, sizeof(__half) * 4 * (size_t)P.h * P.nx, s->stream));
     }
     CU(cudaMalloc(&s->d_mass, sizeof(double)));
+    s->mixed.warps_per_row = (d.nx + 127) / 128;
+    s->mixed.total = (uint32_t)s->mixed.warps_per_row * (uint32_t)std::max(P.h - 2, 0);
+    if (s->mixed.total > 0) {
+        CU(cudaMalloc(&s->mixed.list, sizeof(uint32_t) * s->mixed.total));
+        CU(cudaMalloc(&s->mixed.count_dev, sizeof(uint32_t)));
+    }
 
     s->canvas_w = d.canvas_w > 0 ? d.canvas_w : d.nx * d.lattice_pixel_size;
     s->canvas_h = d.canvas_h > 0 ? d.canvas_h : d.ny * d.lattice_pixel_size;

@@ -55,7 +55,8 @@ struct SlabParams {
     size_t up_plane;   // plane stride of the memory `up` points into
     size_t dn_plane;
     uint8_t *cls;      // [l*pitch + x]
-    uint8_t *nbr;      // bit (i-1) set: cell is strictly interior and cell+e_i is solid
+    uint8_t *nbr;      // fluid cell: bit (i-1) set = strictly interior and cell+e_i is solid (bounce);
+                       // solid cell: bit (k-1) set = slot k is dead (its only reader is solid too)
     LatticeInfo *info; // (h+2) rows of nx: row 0 = halo y0-1, rows 1..h owned, row h+1 = halo
     __half *macro16;   // h*nx texels of 4 halfs, or nullptr
     float *macro32;    // 3 planes of h*nx f32 (u.x,u.y,rho), or nullptr
@@ -181,6 +182,16 @@ __device__ __forceinline__ void accel_update(const SlabParams &P, int x, int l, 
     fy = in.vy;
 }
 
+// Solid cell: write the zeros the reference holds in slots nobody reads (see k_derive), so the
+// destination buffer is written in whole sectors.  Slot 0 of a strictly interior solid is zeroed by
+// boundary.wgsl:28-31 (i = 0: n = cell itself) as well.
+__device__ __forceinline__ void zero_dead_slots(const SlabParams &P, float *wc, uint32_t dead, int x, int y) {
+    if (x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1) wc[0] = 0.0f;
+#pragma unroll
+    for (int k = 1; k < 9; k++)
+        if ((dead >> (k - 1)) & 1u) wc[(size_t)k * P.plane] = 0.0f;
+}
+
 // One cell of the fused step, generic in every respect: periodic wrap in x, neighbour rows
 // in y, bounce-back scatter, accelerate cells.  MODE: 0 = full step, 1 = macro only (no
 // collision/stores/info mutation; used by the on-demand field read).
@@ -194,6 +205,7 @@ __device__ __forceinline__ void update_cell(const SlabParams &P, int rb, int x, 
     const uint8_t c = P.cls[cl];
     if (c == CLS_SOLID) {
         if (MODE == 1 || P.macro16 || P.macro32) store_macro(P, x, l, 0.0f, 0.0f, 0.0f, 0.0f);
+        if (MODE == 0) zero_dead_slots(P, P.f[rb ^ 1] + cl, P.nbr[cl], x, P.y0 + l);
         return;
     }
     const int xm = (x == 0) ? P.nx - 1 : x - 1;      // layout_and_fn.wgsl:40-44

@@ -58,8 +58,21 @@ __global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabPara
     const int m = row[x].material;
     const int y = P.y0 + l;
     uint8_t nb = 0;
-    // boundary.wgsl:19 — only strictly interior cells ever receive a bounce-back
-    if (x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1) {
+    const bool solid = (m == 2 || m == 4);
+    if (solid) {
+        // For a solid cell the byte lists its DEAD slots: slot k is only ever read by the cell at
+        // wrap(cell + e_k); if that cell is solid too, nobody reads the slot and the reference holds 0
+        // there (boundary.wgsl:28-31 moves zeros between adjacent solids).  The step writes those zeros
+        // so that whole 32-byte sectors of the destination buffer get written (no DRAM fill reads).
+#pragma unroll
+        for (int i = 1; i < 9; i++) {
+            int xx = x + kEx[i];
+            if (xx < 0) xx = P.nx - 1; else if (xx >= P.nx) xx = 0;
+            const int mm = row[(ptrdiff_t)kEy[i] * P.nx + xx].material; // halo rows hold the wrapped rows
+            if (mm == 2 || mm == 4) nb |= (uint8_t)(1u << (i - 1));
+        }
+    } else if (x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1) {
+        // boundary.wgsl:19 — only strictly interior cells ever receive a bounce-back
 #pragma unroll
         for (int i = 1; i < 9; i++) {
             const int mm = row[(ptrdiff_t)kEy[i] * P.nx + x + kEx[i]].material;
@@ -67,7 +80,7 @@ __global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabPara
         }
     }
     uint8_t c;
-    if (m == 2 || m == 4) c = CLS_SOLID;
+    if (solid) c = CLS_SOLID;
     else if (m == 3 || m == 6) c = CLS_ACCEL;
     else c = nb ? CLS_FLUID_NB : CLS_FLUID;
     const size_t cl = (size_t)l * P.pitch + x;
