@@ -299,7 +299,7 @@ def main():
         l_lo = (node2.rows - rows) // 2
         patch[:] = node2.read_lattice_info()[l_lo * nx:(l_lo + rows) * nx]  # unchanged rows: same mask, real traffic
         off = (node2.y0 + l_lo) * nx * 16
-        per_call = 2 if kind == "frames" else 1
+        per_call = 2  # one host call = one FluidSimulator::compute frame = 2 lattice updates (fluid_simulator.rs:223-231)
         n_part = fs2.particles_num[0] * fs2.particles_num[1] if fs2 is not None else 0
         parts_t = torch.empty(max(n_part, 1) * 24, dtype=torch.uint8).pin_memory()
         parts = parts_t.numpy()
@@ -310,7 +310,7 @@ def main():
                 check(lib.lbm_compute_frames(node2._h, 1), node2._h)
                 check(lib.lbm_particles_read(node2._h, ptr(parts), n_part), node2._h)
             else:
-                check(lib.lbm_step_n(node2._h, 1), node2._h)
+                check(lib.lbm_compute_frames(node2._h, 1), node2._h)
             check(lib.lbm_read_macro(node2._h, MACRO_RGBA16F, ptr(macro)), node2._h)
 
         for _ in range(3):
@@ -330,8 +330,10 @@ def main():
                "d2h_bytes_per_step": (int(macro.nbytes) + (n_part * 24 if kind == "frames" else 0)) * world // per_call,
                "steps": args.e2e_steps * per_call,
                "what": ("per host call, per rank: lbm_write_lattice_info(56-row LatticeInfo patch from pinned host memory) + "
-                        + ("lbm_compute_frames(1) [2 updates + 2 particle updates] + lbm_particles_read + "
-                           if kind == "frames" else "lbm_step_n(1) (macro texture written by the step) + ")
+                        + ("lbm_compute_frames(1) [= FluidSimulator::compute: 2 updates + 2 particle updates] + "
+                           "lbm_particles_read + " if kind == "frames" else
+                           "lbm_compute_frames(1) [= FluidSimulator::compute: 2 updates, macro texture written by "
+                           "each] + ")
                         + "lbm_read_macro(RGBA16F field of the slab -> pinned host memory); synchronous calls, "
                           "wall clock, max over ranks")}
         barrier(node2)

@@ -77,6 +77,8 @@ struct LbmSim {
     // per-launch host cost and most of the inter-kernel gap; rebuilt whenever a kernel parameter changes
     cudaGraphExec_t graph_steps[2] = {nullptr, nullptr}; // indexed by the swap index of the first step
     cudaGraphExec_t graph_frame = nullptr;
+    uint64_t graph_steps_kernels[2] = {0, 0}; // kernels inside each captured graph (gpu_launches accounting)
+    uint64_t graph_frame_kernels = 0;
     std::string err;
 };
 
@@ -218,13 +220,14 @@ int launch_particles(LbmSim *s) {
 
 // Captures `body` (kernel launches on s->stream) into an executable graph.
 template <typename F>
-int capture_graph(LbmSim *s, cudaGraphExec_t *out, F body) {
+int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
     const uint64_t launches = s->launches, since = s->steps_since_reset;
     const unsigned int step_no = s->sync.step_no;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = body();
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(s->stream, &g);
+    *kernels = s->launches - launches;
     s->launches = launches; // nothing ran yet
     s->steps_since_reset = since;
     s->sync.step_no = step_no;
@@ -511,7 +514,7 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
         cudaGraphExec_t &g = s->graph_steps[s->swap];
         if (!g) {
             const int first = s->swap;
-            rc = capture_graph(s, &g, [&]() {
+            rc = capture_graph(s, &g, &s->graph_steps_kernels[s->swap], [&]() {
                 int r = LBM_OK;
                 for (int i = 0; i < kGraphSteps && r == LBM_OK; i++) r = launch_step(s, first ^ (i & 1));
                 return r;
@@ -524,7 +527,7 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
         cudaGraphExec_t g = s->graph_steps[s->swap];
         for (; left >= kGraphSteps; left -= kGraphSteps) { // an even number of steps: swap index unchanged
             CU(cudaGraphLaunch(g, s->stream));
-            s->launches += kGraphSteps;
+            s->launches += s->graph_steps_kernels[s->swap];
             s->steps_since_reset += kGraphSteps;
             s->sync.step_no += kGraphSteps;
         }
@@ -560,15 +563,14 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
     };
     const bool use_graph = graphs_enabled(s) && n_frames >= 4;
     if (use_graph && !s->graph_frame) {
-        rc = capture_graph(s, &s->graph_frame, frame);
+        rc = capture_graph(s, &s->graph_frame, &s->graph_frame_kernels, frame);
         if (rc) return rc;
     }
-    const uint64_t per_frame = with_particles ? 4 : 2;
     CU(cudaEventRecord(s->ev0, s->stream));
     for (int f = 0; f < n_frames; f++) {
         if (use_graph) {
             CU(cudaGraphLaunch(s->graph_frame, s->stream));
-            s->launches += per_frame;
+            s->launches += s->graph_frame_kernels;
             s->steps_since_reset += 2;
             s->sync.step_no += 2;
         } else {
