@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=None, help="BASELINE.json config 1..5 (default 2 at N=1, 3 at N>1)")
+    ap.add_argument("--aa", action="store_true", help="AA-pattern in-place variant (single copy of the distributions)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels one by one instead of CUDA graphs")
     ap.add_argument("--lattice", type=int, nargs=2, default=None, metavar=("NX", "NY"), help="override the workload")
     ap.add_argument("--e2e-steps", type=int, default=20)
@@ -232,7 +233,8 @@ def main():
     setting = sb.SettingObj(animation_type=W.POISEUILLE, particles_count=1000000 if porous else 10000)
     canvas = (nx * 2, ny * 2)
     preset = sb.PRESET_POROUS if porous else W.POISEUILLE
-    base_flags = (sb.FLAG_KERNEL_GENERIC if args.generic else 0) | (sb.FLAG_NO_GRAPH if args.no_graph else 0)
+    base_flags = ((sb.FLAG_KERNEL_GENERIC if args.generic else 0) | (sb.FLAG_NO_GRAPH if args.no_graph else 0)
+                  | (sb.FLAG_AA if args.aa else 0))
 
     def make_sim(flags):
         """(slab or None, node, FluidSimulator or None)"""
@@ -350,7 +352,8 @@ def main():
             "config": {"workload": name, "baseline_config": config, "lattice": [nx, ny], "tau": 0.56,
                        "l2": "inputs_larger_than_l2" if sites * 72 / world > 2.6e8 else "lattice fits in L2 (the reference's own size)",
                        "cuda_graphs": not args.no_graph and world == 1,
-                       "kernel": "k_step_generic" if args.generic else "k_step_vec", "state": "A/B ping-pong SoA planes",
+                       "kernel": "k_step_generic" if args.generic else ("k_aa_pull/k_aa_local" if args.aa else "k_step_vec"),
+                       "state": "AA in-place, one copy of the SoA planes" if args.aa else "A/B ping-pong SoA planes",
                        "total_mass_after": mass},
             "clocks": clocks,
             "gpu_launches": launches,

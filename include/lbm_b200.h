@@ -68,6 +68,11 @@ typedef enum LbmStatus {
                                           collide_stream.wgsl:74 (needed by the tracer particles).
                                           Off: the field is produced on demand by lbm_read_macro. */
 #define LBM_FLAG_KERNEL_GENERIC   0x2u /* force the one-thread-per-cell kernel (A/B testing) */
+#define LBM_FLAG_AA               0x8u /* AA-pattern in-place streaming: ONE copy of the distributions instead of
+                                          the A/B ping-pong pair (half the memory, same traffic).  Single slab
+                                          only; lbm_read_distributions / lbm_total_mass serve the current state
+                                          (which == lbm_swap_index), canonicalised to the reference layout; the
+                                          previous buffer and the on-demand macro field do not exist. */
 #define LBM_FLAG_NO_GRAPH         0x4u /* launch every kernel individually instead of replaying CUDA
                                           graphs of 16 steps / one frame (A/B testing) */
 

@@ -100,6 +100,7 @@ pub const LBM_OK: c_int = 0;
 pub const LBM_FLAG_MACRO_EVERY_STEP: u32 = 0x1;
 pub const LBM_FLAG_KERNEL_GENERIC: u32 = 0x2;
 pub const LBM_FLAG_NO_GRAPH: u32 = 0x4;
+pub const LBM_FLAG_AA: u32 = 0x8;
 pub const LBM_MACRO_F32_PLANES: i32 = 0;
 pub const LBM_MACRO_RGBA16F: i32 = 1;
 

@@ -17,6 +17,7 @@ OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED
 FLAG_MACRO_EVERY_STEP = 0x1
 FLAG_KERNEL_GENERIC = 0x2
 FLAG_NO_GRAPH = 0x4
+FLAG_AA = 0x8
 MACRO_F32_PLANES, MACRO_RGBA16F = 0, 1
 PRESET_POROUS = 100
 

@@ -14,6 +14,7 @@
 #include "lbm_kernels.cuh"
 #include "lbm_particles.cuh"
 #include "lbm_step_vec.cuh"
+#include "lbm_aa.cuh"
 
 using namespace lbm;
 
@@ -54,6 +55,8 @@ struct LbmSim {
     double *d_mass = nullptr;
     float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
     __half *scratch16 = nullptr; // RGBA16F texels for the on-demand macro read
+    float *scratch_dense = nullptr; // 9 dense planes: canonical view of an AA state in its shifted layout
+    bool aa = false;
     uint64_t steps_since_reset = 0;
     bool have_uniform = false;
     bool have_info = false;
@@ -170,7 +173,11 @@ __global__ void k_macro_after_init(const __grid_constant__ SlabParams P) {
 
 int launch_step(LbmSim *s, int rb) {
     int rc = LBM_OK;
-    if (s->d.flags & LBM_FLAG_KERNEL_GENERIC) {
+    if (s->aa) {
+        cudaError_t e = launch_step_aa(s->P, rb, s->stream); // rb = parity: 0 pulls (N->S), 1 is local (S->N)
+        if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_aa_* failed: %s", cudaGetErrorString(e));
+        s->launches++;
+    } else if (s->d.flags & LBM_FLAG_KERNEL_GENERIC) {
         const bool multi = s->d.world > 1;
         if (multi) {
             k_wait<<<1, 32, 0, s->stream>>>(s->sync);
@@ -199,6 +206,14 @@ int ready_to_step(LbmSim *s) {
     if (!s->have_info) return fail(s, LBM_ERR_STATE, "no lattice info uploaded or generated");
     if (s->d.world > 1 && !s->attached) return fail(s, LBM_ERR_STATE, "slab of a %d-slab lattice is not attached to its neighbours (lbm_ipc_attach)", s->d.world);
     return LBM_OK;
+}
+
+int aa_canonical(LbmSim *s) {
+    const SlabParams &P = s->P;
+    if (!s->scratch_dense) CU(cudaMalloc(&s->scratch_dense, sizeof(float) * 9 * (size_t)P.h * P.nx));
+    dim3 block(64, 4);
+    k_aa_canonical<<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(P, s->scratch_dense);
+    return check_launch(s, "k_aa_canonical");
 }
 
 constexpr int kGraphSteps = 16;
@@ -280,6 +295,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->P.macro16);
     cudaFree(s->scratch32);
     cudaFree(s->scratch16);
+    cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
     cudaFree(s->mixed.list);
     cudaFree(s->mixed.count_dev);
@@ -324,11 +340,15 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     P.pitch = (int)align_up((size_t)d.nx, 32);
     P.plane = align_up((size_t)P.h * P.pitch, 32);
 
+    s->aa = (d.flags & LBM_FLAG_AA) != 0;
+    if (s->aa && d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "LBM_FLAG_AA is single-slab only");
+    if (s->aa && (d.flags & LBM_FLAG_KERNEL_GENERIC)) return fail(s, LBM_ERR_UNSUPPORTED, "LBM_FLAG_AA has its own kernels");
     const size_t fbytes = align_up(sizeof(float) * 9 * P.plane, 256);
+    const size_t n_buf = s->aa ? 1 : 2;
     s->f_off[0] = 0;
-    s->f_off[1] = fbytes;
-    s->flag_off = 2 * fbytes;
-    s->arena_bytes = 2 * fbytes + 256;
+    s->f_off[1] = s->aa ? 0 : fbytes;
+    s->flag_off = n_buf * fbytes;
+    s->arena_bytes = n_buf * fbytes + 256;
     CU(cudaMalloc(&s->arena, s->arena_bytes));
     CU(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
     P.f[0] = reinterpret_cast<float *>(s->arena + s->f_off[0]);
@@ -497,6 +517,8 @@ extern "C" int lbm_step(LbmSim *s, int32_t swap_index) {
     if (swap_index != 0 && swap_index != 1) return fail(s, LBM_ERR_INVALID_ARG, "swap_index must be 0 or 1");
     int rc = ready_to_step(s);
     if (rc) return rc;
+    if (s->aa && swap_index != s->swap)
+        return fail(s, LBM_ERR_STATE, "in-place (AA) state is in layout %d: the next step must use swap_index %d", s->swap, s->swap);
     CU(cudaSetDevice(s->device));
     rc = launch_step(s, swap_index);
     if (rc) return rc;
@@ -607,6 +629,16 @@ extern "C" int lbm_read_distributions(LbmSim *s, int32_t which, float *dst) {
     CU(cudaSetDevice(s->device));
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
+    if (s->aa) {
+        if (which != s->swap) return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: only the current state (which = %d) exists", s->swap);
+        if (s->swap == 1) { // shifted layout: canonicalise to the reference layout first
+            int rc = aa_canonical(s);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(dst, s->scratch_dense, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            return LBM_OK;
+        }
+    }
     for (int i = 0; i < 9; i++)
         CU(cudaMemcpy2DAsync(dst + i * n, sizeof(float) * P.nx, P.f[which] + i * P.plane, sizeof(float) * P.pitch,
                              sizeof(float) * P.nx, P.h, cudaMemcpyDeviceToHost, s->stream));
@@ -616,6 +648,8 @@ extern "C" int lbm_read_distributions(LbmSim *s, int32_t which, float *dst) {
 
 extern "C" int lbm_write_distributions(LbmSim *s, int32_t which, const float *src) {
     if (!s || !src || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
+    if (s->aa && (which != 0 || s->swap != 0))
+        return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: distributions can only be written as buffer 0 in the natural layout (after lbm_reset or an even number of steps)");
     CU(cudaSetDevice(s->device));
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
@@ -638,6 +672,8 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
         CU(cudaStreamSynchronize(s->stream));
         return LBM_OK;
     }
+    if (s->aa && s->steps_since_reset != 0)
+        return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: the step overwrites its inputs, create it with LBM_FLAG_MACRO_EVERY_STEP to read the field");
     // On demand: the buffer the last step read is still intact (A/B ping-pong), so pulling from it
     // again yields exactly the (rho, u) that step computed (collide_stream.wgsl:43-74).
     int rc = ready_to_step(s);
@@ -684,8 +720,16 @@ extern "C" int lbm_total_mass(LbmSim *s, int32_t which, double *out) {
     if (!s || !out || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
     CU(cudaSetDevice(s->device));
     CU(cudaMemsetAsync(s->d_mass, 0, sizeof(double), s->stream));
-    k_mass<<<148 * 4, 256, 0, s->stream>>>(s->P, which, s->d_mass);
-    int rc = check_launch(s, "k_mass");
+    int rc;
+    if (s->aa && which != s->swap) return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: only the current state (which = %d) exists", s->swap);
+    if (s->aa && s->swap == 1) {
+        if ((rc = aa_canonical(s))) return rc;
+        k_sum_dense<<<148 * 4, 256, 0, s->stream>>>(s->scratch_dense, (size_t)9 * s->P.h * s->P.nx, s->d_mass);
+        rc = check_launch(s, "k_sum_dense");
+    } else {
+        k_mass<<<148 * 4, 256, 0, s->stream>>>(s->P, which, s->d_mass);
+        rc = check_launch(s, "k_mass");
+    }
     if (rc) return rc;
     CU(cudaMemcpyAsync(out, s->d_mass, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));

@@ -28,9 +28,15 @@ enum : uint8_t {
 };
 
 // D2Q9 lattice vectors (fluid/mod.rs:39-52), fixed; lbm_write_uniform rejects anything else.
-__device__ __constant__ const int kEx[9] = {0, 1, 0, -1, 0, 1, -1, -1, 1};
-__device__ __constant__ const int kEy[9] = {0, 0, -1, 0, 1, -1, -1, 1, 1};
-__device__ __constant__ const int kInv[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+// constexpr functions rather than __constant__ tables: under full unrolling they fold to immediates
+__host__ __device__ constexpr int dir_ex(int i) { return (i == 1 || i == 5 || i == 8) ? 1 : ((i == 3 || i == 6 || i == 7) ? -1 : 0); }
+__host__ __device__ constexpr int dir_ey(int i) { return (i == 4 || i == 7 || i == 8) ? 1 : ((i == 2 || i == 5 || i == 6) ? -1 : 0); }
+__host__ __device__ constexpr int dir_inv(int i) { return i == 0 ? 0 : (i <= 2 ? i + 2 : (i <= 4 ? i - 2 : (i <= 6 ? i + 2 : i - 2))); }
+static_assert(dir_inv(1) == 3 && dir_inv(2) == 4 && dir_inv(3) == 1 && dir_inv(4) == 2 && dir_inv(5) == 7 &&
+                  dir_inv(6) == 8 && dir_inv(7) == 5 && dir_inv(8) == 6, "fluid/mod.rs:50-52");
+static_assert(dir_ex(5) == 1 && dir_ey(5) == -1 && dir_ex(6) == -1 && dir_ey(6) == -1 && dir_ex(7) == -1 &&
+                  dir_ey(7) == 1 && dir_ex(8) == 1 && dir_ey(8) == 1 && dir_ex(2) == 0 && dir_ey(2) == -1 && dir_ey(4) == 1,
+              "fluid/mod.rs:39-49");
 
 struct Coef {
     float omega;
@@ -122,7 +128,7 @@ __device__ __forceinline__ void collide_forced(const Coef &k, float rho, float u
     const float usqr = fmul(1.5f, fadd(fmul(ux, ux), fmul(uy, uy)));
 #pragma unroll
     for (int i = 0; i < 9; i++) {
-        const float ex = (float)kEx[i], ey = (float)kEy[i];
+        const float ex = (float)dir_ex(i), ey = (float)dir_ey(i);
         const float eu = fadd(fmul(ex, ux), fmul(ey, uy));
         const float feq = fmul(fmul(rho, k.w[i]),
                                fsub(fadd(fadd(1.0f, fmul(3.0f, eu)), fmul(4.5f, fmul(eu, eu))), usqr));
@@ -192,6 +198,32 @@ __device__ __forceinline__ void zero_dead_slots(const SlabParams &P, float *wc, 
         if ((dead >> (k - 1)) & 1u) wc[(size_t)k * P.plane] = 0.0f;
 }
 
+// Moments, inlet / force handling, BGK collision and the macro store of one non-solid cell whose nine
+// distributions have been pulled into f (collide_stream.wgsl:43-87 after the pull).  In place.
+template <int MODE>
+__device__ __forceinline__ void collide_cell(const SlabParams &P, uint8_t c, uint8_t nb, int x, int l, float (&f)[9]) {
+    const size_t cl = (size_t)l * P.pitch + x;
+    float rho, ux, uy;
+    moments(f, rho, ux, uy);
+    if (MODE == 0 && c == CLS_FLIPPED) P.cls[cl] = nb ? CLS_FLUID_NB : CLS_FLUID;
+    if (c == CLS_ACCEL || (MODE == 1 && c == CLS_FLIPPED)) {
+        float fx, fy;
+        if (MODE == 0) {
+            accel_update(P, x, l, fx, fy);
+        } else {
+            const LatticeInfo in = P.info[(size_t)(l + 1) * P.nx + x];
+            fx = in.vx;
+            fy = in.vy;
+        }
+        ux = fdiv(fmul(fx, 0.5f), rho);             // :66
+        uy = fdiv(fmul(fy, 0.5f), rho);
+        if (MODE == 0) collide_forced(P.k, rho, ux, uy, fx, fy, f);
+    } else if (MODE == 0) {
+        collide_plain(P.k, rho, ux, uy, f);
+    }
+    if (MODE == 1 || P.macro16 || P.macro32) store_macro(P, x, l, ux, uy, rho, 1.0f);
+}
+
 // One cell of the fused step, generic in every respect: periodic wrap in x, neighbour rows
 // in y, bounce-back scatter, accelerate cells.  MODE: 0 = full step, 1 = macro only (no
 // collision/stores/info mutation; used by the on-demand field read).
@@ -223,26 +255,8 @@ __device__ __forceinline__ void update_cell(const SlabParams &P, int rb, int x, 
     f[6] = rd.p[6 * rd.plane + xp];
     f[7] = ru.p[7 * ru.plane + xp];
     f[8] = ru.p[8 * ru.plane + xm];
-    float rho, ux, uy;
-    moments(f, rho, ux, uy);
     const uint8_t nb = (c == CLS_FLUID) ? 0 : P.nbr[cl];
-    if (MODE == 0 && c == CLS_FLIPPED) P.cls[cl] = nb ? CLS_FLUID_NB : CLS_FLUID;
-    if (c == CLS_ACCEL || (MODE == 1 && c == CLS_FLIPPED)) {
-        float fx, fy;
-        if (MODE == 0) {
-            accel_update(P, x, l, fx, fy);
-        } else {
-            const LatticeInfo in = P.info[(size_t)(l + 1) * P.nx + x];
-            fx = in.vx;
-            fy = in.vy;
-        }
-        ux = fdiv(fmul(fx, 0.5f), rho);             // :66
-        uy = fdiv(fmul(fy, 0.5f), rho);
-        if (MODE == 0) collide_forced(P.k, rho, ux, uy, fx, fy, f);
-    } else if (MODE == 0) {
-        collide_plain(P.k, rho, ux, uy, f);
-    }
-    if (MODE == 1 || P.macro16 || P.macro32) store_macro(P, x, l, ux, uy, rho, 1.0f);
+    collide_cell<MODE>(P, c, nb, x, l, f);
     if (MODE == 1) return;
 
     const int wb = rb ^ 1;
@@ -256,8 +270,8 @@ __device__ __forceinline__ void update_cell(const SlabParams &P, int rb, int x, 
 #pragma unroll
     for (int i = 1; i < 9; i++) {
         if ((nb >> (i - 1)) & 1) {
-            const RowRef rt = row_ref(P, wb, l + kEy[i]);
-            rt.p[(size_t)kInv[i] * rt.plane + (x + kEx[i])] = f[i];
+            const RowRef rt = row_ref(P, wb, l + dir_ey(i));
+            rt.p[(size_t)dir_inv(i) * rt.plane + (x + dir_ex(i))] = f[i];
             w0[(size_t)i * P.plane] = 0.0f;
         } else {
             w0[(size_t)i * P.plane] = f[i];

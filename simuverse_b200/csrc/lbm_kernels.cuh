@@ -27,18 +27,19 @@ __global__ void __launch_bounds__(256) k_init(const __grid_constant__ SlabParams
     LatticeInfo in = *ip;
     const size_t cl = (size_t)l * P.pitch + x;
     float *b0 = P.f[0] + cl, *b1 = P.f[1] + cl;
+    const bool two = P.f[1] != P.f[0]; // the in-place (AA) variant keeps only collide_cell = buffer 0
     const bool solid = in.material == 2 || in.material == 4;
     if (solid) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) { b0[i * P.plane] = 0.0f; b1[i * P.plane] = 0.0f; }
+        for (int i = 0; i < 9; i++) { b0[i * P.plane] = 0.0f; if (two) b1[i * P.plane] = 0.0f; }
     } else {
 #pragma unroll
-        for (int i = 0; i < 9; i++) { b0[i * P.plane] = P.k.w[i]; b1[i * P.plane] = 0.0f; }
+        for (int i = 0; i < 9; i++) { b0[i * P.plane] = P.k.w[i]; if (two) b1[i * P.plane] = 0.0f; }
         if (P.k.fluid_ty == 0) { // isPoiseuilleFlow(): bias along +x (init.wgsl:39-43)
             const float temp = fmul(P.k.w[3], 0.5f);
             const float f1 = fadd(P.k.w[1], temp);
             b0[1 * P.plane] = f1; b0[3 * P.plane] = temp;
-            b1[1 * P.plane] = f1; b1[3 * P.plane] = temp;
+            if (two) { b1[1 * P.plane] = f1; b1[3 * P.plane] = temp; }
         }
     }
     if ((in.material == 3 || in.material == 6) && in.block_iter > 0) { // init.wgsl:51-59
@@ -66,23 +67,36 @@ __global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabPara
         // so that whole 32-byte sectors of the destination buffer get written (no DRAM fill reads).
 #pragma unroll
         for (int i = 1; i < 9; i++) {
-            int xx = x + kEx[i];
+            int xx = x + dir_ex(i);
             if (xx < 0) xx = P.nx - 1; else if (xx >= P.nx) xx = 0;
-            const int mm = row[(ptrdiff_t)kEy[i] * P.nx + xx].material; // halo rows hold the wrapped rows
+            const int mm = row[(ptrdiff_t)dir_ey(i) * P.nx + xx].material; // halo rows hold the wrapped rows
             if (mm == 2 || mm == 4) nb |= (uint8_t)(1u << (i - 1));
         }
     } else if (x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1) {
         // boundary.wgsl:19 — only strictly interior cells ever receive a bounce-back
 #pragma unroll
         for (int i = 1; i < 9; i++) {
-            const int mm = row[(ptrdiff_t)kEy[i] * P.nx + x + kEx[i]].material;
+            const int mm = row[(ptrdiff_t)dir_ey(i) * P.nx + x + dir_ex(i)].material;
             if (mm == 2 || mm == 4) nb |= (uint8_t)(1u << (i - 1));
+        }
+    }
+    bool ring_touches_solid = false;
+    if (!solid && !(x > 0 && x < P.nx - 1 && y > 0 && y < P.ny - 1)) {
+        // a ring cell never bounces (nb stays 0) but may pull from a solid neighbour, possibly across the
+        // periodic wrap: keep its warp out of the pure path, whose in-place (AA) variant assumes that no
+        // cell within one step of a pure warp is solid
+#pragma unroll
+        for (int i = 1; i < 9; i++) {
+            int xx = x + dir_ex(i);
+            if (xx < 0) xx = P.nx - 1; else if (xx >= P.nx) xx = 0;
+            const int mm = row[(ptrdiff_t)dir_ey(i) * P.nx + xx].material;
+            ring_touches_solid |= (mm == 2 || mm == 4);
         }
     }
     uint8_t c;
     if (solid) c = CLS_SOLID;
     else if (m == 3 || m == 6) c = CLS_ACCEL;
-    else c = nb ? CLS_FLUID_NB : CLS_FLUID;
+    else c = (nb || ring_touches_solid) ? CLS_FLUID_NB : CLS_FLUID;
     const size_t cl = (size_t)l * P.pitch + x;
     P.cls[cl] = c;
     P.nbr[cl] = nb;
@@ -141,6 +155,21 @@ __global__ void __launch_bounds__(256) k_generate(const __grid_constant__ SlabPa
     LatticeInfo o;
     o.material = material; o.block_iter = -1; o.vx = vx; o.vy = 0.0f;
     P.info[(size_t)r * nx + x] = o;
+}
+
+// f64 sum of a dense array (canonicalised AA state)
+__global__ void __launch_bounds__(256) k_sum_dense(const float *p, size_t n, double *out) {
+    double s = 0.0;
+    for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) s += (double)p[c];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        s = ws[threadIdx.x];
+        for (int o = 4; o > 0; o >>= 1) s += __shfl_down_sync(0xffu, s, o);
+        if (threadIdx.x == 0) atomicAdd(out, s);
+    }
 }
 
 // ------------------------------------------------------------------ total mass (f64)

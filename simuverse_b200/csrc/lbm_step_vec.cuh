@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kVecThreads) k_step_mixed(const __grid_constan
             for (int i = 1; i < 9; i++) {
                 const bool bounce = (nb >> (i - 1)) & 1u;
                 wc[(size_t)i * pl] = bounce ? 0.0f : f[i];
-                if (bounce) wc[(ptrdiff_t)((size_t)kInv[i] * pl) + (ptrdiff_t)kEy[i] * P.pitch + kEx[i]] = f[i];
+                if (bounce) wc[(ptrdiff_t)((size_t)dir_inv(i) * pl) + (ptrdiff_t)dir_ey(i) * P.pitch + dir_ex(i)] = f[i];
             }
         }
     }
