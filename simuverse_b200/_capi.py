@@ -11,7 +11,8 @@ import os
 from .wire import FieldUniform, LbmUniform, ParticleUniform
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_native", "liblbm_b200.so")
+# LBM_B200_LIB: tuning experiments load an alternative in-tree build of the SAME sources (never a fallback)
+LIB_PATH = os.environ.get("LBM_B200_LIB") or os.path.join(_HERE, "_native", "liblbm_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OUT_OF_MEMORY, ERR_UNSUPPORTED, ERR_STATE = range(7)
 FLAG_MACRO_EVERY_STEP = 0x1

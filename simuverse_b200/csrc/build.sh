@@ -4,6 +4,7 @@ set -euo pipefail
 here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 out="$here/../_native"
 mkdir -p "$out"
+name="${LBM_OUT_NAME:-liblbm_b200.so}"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 HOSTCXX="${LBM_HOSTCXX:-/usr/bin/g++}"
 [ -x "$HOSTCXX" ] || HOSTCXX=g++
@@ -13,4 +14,4 @@ set -x
   -fmad=false -prec-div=true -prec-sqrt=true -ftz=false \
   -Xptxas -v -Xcompiler -fPIC,-O2,-ffp-contract=off,-Wall \
   -shared -cudart static \
-  -o "$out/liblbm_b200.so" "$here/lbm_b200.cu" "$here/host_logic.cpp" ${LBM_EXTRA_NVCC_FLAGS:-}
+  -o "$out/$name" "$here/lbm_b200.cu" "$here/host_logic.cpp" ${LBM_EXTRA_NVCC_FLAGS:-}

@@ -24,6 +24,10 @@
 
 #include "lbm_step_vec.cuh"
 
+#ifndef LBM_AA_MIN_CTAS
+#define LBM_AA_MIN_CTAS 7
+#endif
+
 namespace lbm {
 
 __device__ __forceinline__ int wrap_x(const SlabParams &P, int x) { return x < 0 ? P.nx - 1 : (x >= P.nx ? 0 : x); }
@@ -108,7 +112,7 @@ __device__ __forceinline__ void aa_cell_local(const SlabParams &P, int x, int l)
 // periodically and take the per-cell path).  A pure warp (k_derive: 128 plain-fluid cells, ring cells that
 // touch a solid excluded) has no solid within one cell of its span, so all its traffic is 128-bit.
 template <bool MACRO>
-__global__ void __launch_bounds__(kVecThreads) k_aa_local(const __grid_constant__ SlabParams P, int tiles_x) {
+__global__ void __launch_bounds__(kVecThreads, LBM_AA_MIN_CTAS) k_aa_local(const __grid_constant__ SlabParams P, int tiles_x) {
     const int l = blockIdx.x / tiles_x;
     const int tile = blockIdx.x - l * tiles_x;
     const int x0 = (tile * kVecThreads + threadIdx.x) * 4;
@@ -145,40 +149,15 @@ __global__ void __launch_bounds__(kVecThreads) k_aa_local(const __grid_constant_
     }
 }
 
-// Vector store of the four values of one direction shifted by +1 in x: cells x0..x0+3 write x0+1..x0+4.
-// Lane t stores the aligned vector [left.w, a, b, c]; its own d goes to lane t+1.  The warp's first lane
-// has no left lane (3 scalar stores), its last lane stores d itself (wrap folded into `last_off`).
-__device__ __forceinline__ void push_right(float *row, int lane, bool last, ptrdiff_t last_off, float a, float b, float c,
-                                           float d) {
-    const float l = __shfl_up_sync(0xffffffffu, d, 1);
-    if (lane == 0) { row[1] = a; row[2] = b; row[3] = c; }
-    else stg4(row, l, a, b, c);
-    if (last) row[last_off] = d;
-}
-// shifted by -1 in x: cells x0..x0+3 write x0-1..x0+2
-__device__ __forceinline__ void push_left(float *row, int lane, bool last, ptrdiff_t first_off, float a, float b, float c,
-                                          float d) {
-    const float r = __shfl_down_sync(0xffffffffu, a, 1);
-    if (last) { row[0] = b; row[1] = c; row[2] = d; }
-    else stg4(row, b, c, d, r);
-    if (lane == 0) row[first_off] = a;
-}
-
 template <bool MACRO>
-__global__ void __launch_bounds__(kVecThreads) k_aa_pull(const __grid_constant__ SlabParams P, int tiles_x) {
+__global__ void __launch_bounds__(kVecThreads, LBM_AA_MIN_CTAS) k_aa_pull(const __grid_constant__ SlabParams P, int tiles_x) {
     const int l = blockIdx.x / tiles_x;
     const int tile = blockIdx.x - l * tiles_x;
     const int x0 = (tile * kVecThreads + threadIdx.x) * 4;
     const int lane = threadIdx.x & 31;
     const int nx = P.nx;
     const bool in_row = x0 < nx;
-    const bool edge_row = (l == 0 || l == P.h - 1);
-    const bool ragged = in_row && (x0 + 4 > nx);
-    Pulled q;
-    q.cw = 1;
-    if (!edge_row) q = pull_row4(P, 0, l, x0, lane, in_row); // rows l-1 .. l+1 exist
-    // warp-uniform: the shifted stores below need every lane of the warp
-    if (edge_row || __any_sync(0xffffffffu, in_row && (q.cw != 0 || ragged))) {
+    if (l == 0 || l == P.h - 1) { // rows that wrap periodically in y: per-cell path
         if (in_row) {
 #pragma unroll 1
             for (int c = 0; c < 4; c++)
@@ -186,64 +165,69 @@ __global__ void __launch_bounds__(kVecThreads) k_aa_pull(const __grid_constant__
         }
         return;
     }
-    // pure warp: in_row may still be false for trailing lanes of the row's last warp (they hold zeros and
-    // must not store); `last` is the last lane that owns cells
-    const bool last = in_row && (lane == 31 || x0 + 4 >= nx);
+    Pulled q = pull_row4(P, 0, l, x0, lane, in_row); // rows l-1 .. l+1 exist
+    // A lane is `plain` when its four cells are plain fluid: it then stores 128-bit vectors whose first /
+    // last element comes from the neighbouring lane.  Any other lane handles its cells one by one and its
+    // neighbours fall back to scalar stores for the element they would have taken from it.  (The location
+    // sets of different cells are disjoint, so the order of all these accesses is free.)
+    const bool plain = in_row && q.cw == 0 && x0 + 4 <= nx;
+    const bool left_plain = __shfl_up_sync(0xffffffffu, plain, 1) && lane > 0;
+    const bool right_plain = __shfl_down_sync(0xffffffffu, plain, 1) && lane < 31;
     float F[4][9] = {{q.v0.x, q.v1.x, q.v2.x, q.v3.x, q.v4.x, q.v5.x, q.v6.x, q.v7.x, q.v8.x},
                      {q.v0.y, q.v1.y, q.v2.y, q.v3.y, q.v4.y, q.v5.y, q.v6.y, q.v7.y, q.v8.y},
                      {q.v0.z, q.v1.z, q.v2.z, q.v3.z, q.v4.z, q.v5.z, q.v6.z, q.v7.z, q.v8.z},
                      {q.v0.w, q.v1.w, q.v2.w, q.v3.w, q.v4.w, q.v5.w, q.v6.w, q.v7.w, q.v8.w}};
     float mrho[4], mux[4], muy[4];
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < 4; c++) { // non-plain lanes compute throw-away values: no divergence before the shuffles
         moments(F[c], mrho[c], mux[c], muy[c]);
         collide_plain(P.k, mrho[c], mux[c], muy[c], F[c]);
+    }
+    // f*_j of cell x goes to A[x+e_j, inv(j)]:
+    //   j = 1 (1,0) -> plane 3 ; j = 5 (1,-1) -> row l-1, plane 7 ; j = 8 (1,1) -> row l+1, plane 6   (x+1)
+    //   j = 3 (-1,0) -> plane 1 ; j = 6 (-1,-1) -> row l-1, plane 8 ; j = 7 (-1,1) -> row l+1, plane 5 (x-1)
+    const float l1 = __shfl_up_sync(0xffffffffu, F[3][1], 1), l5 = __shfl_up_sync(0xffffffffu, F[3][5], 1),
+                l8 = __shfl_up_sync(0xffffffffu, F[3][8], 1);
+    const float r3 = __shfl_down_sync(0xffffffffu, F[0][3], 1), r6 = __shfl_down_sync(0xffffffffu, F[0][6], 1),
+                r7 = __shfl_down_sync(0xffffffffu, F[0][7], 1);
+    if (!in_row) return;
+    if (!plain) {
+#pragma unroll 1
+        for (int c = 0; c < 4; c++)
+            if (x0 + c < nx) aa_cell_pull(P, x0 + c, l);
+        return;
     }
     const size_t pl = P.plane;
     float *a0 = P.f[0] + (size_t)l * P.pitch + x0;  // own row
     float *au = a0 - P.pitch, *ad = a0 + P.pitch;    // rows l-1, l+1
-    const ptrdiff_t wrap_hi = (x0 + 4 >= nx) ? -(ptrdiff_t)x0 : (ptrdiff_t)4;      // column of cell x0+4
-    const ptrdiff_t wrap_lo = (x0 == 0) ? (ptrdiff_t)(nx - 1) : (ptrdiff_t)-1;      // column of cell x0-1
-    // f*_j of cell x goes to A[x+e_j, inv(j)].  Trailing lanes (!in_row) only take part in the shuffles.
-    // j = 0, 2, 4: no x shift
-    if (in_row) {
-        stg4(a0, F[0][0], F[1][0], F[2][0], F[3][0]);
-        stg4(au + 4 * pl, F[0][2], F[1][2], F[2][2], F[3][2]); // j=2: e=(0,-1) -> row l-1, plane inv(2)=4
-        stg4(ad + 2 * pl, F[0][4], F[1][4], F[2][4], F[3][4]); // j=4: e=(0,+1) -> row l+1, plane inv(4)=2
+    const ptrdiff_t hi = (x0 + 4 >= nx) ? -(ptrdiff_t)x0 : (ptrdiff_t)4;      // column of cell x0+4 (periodic)
+    const ptrdiff_t lo = (x0 == 0) ? (ptrdiff_t)(nx - 1) : (ptrdiff_t)-1;      // column of cell x0-1
+    stg4(a0, F[0][0], F[1][0], F[2][0], F[3][0]);
+    stg4(au + 4 * pl, F[0][2], F[1][2], F[2][2], F[3][2]); // j=2: e=(0,-1) -> row l-1, plane inv(2)=4
+    stg4(ad + 2 * pl, F[0][4], F[1][4], F[2][4], F[3][4]); // j=4: e=(0,+1) -> row l+1, plane inv(4)=2
+    float *p1 = a0 + 3 * pl, *p5 = au + 7 * pl, *p8 = ad + 6 * pl;
+    if (left_plain) {
+        stg4(p1, l1, F[0][1], F[1][1], F[2][1]);
+        stg4(p5, l5, F[0][5], F[1][5], F[2][5]);
+        stg4(p8, l8, F[0][8], F[1][8], F[2][8]);
+    } else {
+        p1[1] = F[0][1]; p1[2] = F[1][1]; p1[3] = F[2][1];
+        p5[1] = F[0][5]; p5[2] = F[1][5]; p5[3] = F[2][5];
+        p8[1] = F[0][8]; p8[2] = F[1][8]; p8[3] = F[2][8];
     }
-    // j = 1 (1,0)->plane 3 ; j = 5 (1,-1)->row l-1, plane 7 ; j = 8 (1,1)->row l+1, plane 6
-    // j = 3 (-1,0)->plane 1 ; j = 6 (-1,-1)->row l-1, plane 8 ; j = 7 (-1,1)->row l+1, plane 5
-    {
-        const float l1 = __shfl_up_sync(0xffffffffu, F[3][1], 1), l5 = __shfl_up_sync(0xffffffffu, F[3][5], 1),
-                    l8 = __shfl_up_sync(0xffffffffu, F[3][8], 1);
-        const float r3 = __shfl_down_sync(0xffffffffu, F[0][3], 1), r6 = __shfl_down_sync(0xffffffffu, F[0][6], 1),
-                    r7 = __shfl_down_sync(0xffffffffu, F[0][7], 1);
-        if (in_row) {
-            float *p1 = a0 + 3 * pl, *p5 = au + 7 * pl, *p8 = ad + 6 * pl;
-            if (lane == 0) {
-                p1[1] = F[0][1]; p1[2] = F[1][1]; p1[3] = F[2][1];
-                p5[1] = F[0][5]; p5[2] = F[1][5]; p5[3] = F[2][5];
-                p8[1] = F[0][8]; p8[2] = F[1][8]; p8[3] = F[2][8];
-            } else {
-                stg4(p1, l1, F[0][1], F[1][1], F[2][1]);
-                stg4(p5, l5, F[0][5], F[1][5], F[2][5]);
-                stg4(p8, l8, F[0][8], F[1][8], F[2][8]);
-            }
-            if (last) { p1[wrap_hi] = F[3][1]; p5[wrap_hi] = F[3][5]; p8[wrap_hi] = F[3][8]; }
-            float *p3 = a0 + 1 * pl, *p6 = au + 8 * pl, *p7 = ad + 5 * pl;
-            if (last) {
-                p3[0] = F[1][3]; p3[1] = F[2][3]; p3[2] = F[3][3];
-                p6[0] = F[1][6]; p6[1] = F[2][6]; p6[2] = F[3][6];
-                p7[0] = F[1][7]; p7[1] = F[2][7]; p7[2] = F[3][7];
-            } else {
-                stg4(p3, F[1][3], F[2][3], F[3][3], r3);
-                stg4(p6, F[1][6], F[2][6], F[3][6], r6);
-                stg4(p7, F[1][7], F[2][7], F[3][7], r7);
-            }
-            if (lane == 0) { p3[wrap_lo] = F[0][3]; p6[wrap_lo] = F[0][6]; p7[wrap_lo] = F[0][7]; }
-        }
+    if (!right_plain) { p1[hi] = F[3][1]; p5[hi] = F[3][5]; p8[hi] = F[3][8]; }
+    float *p3 = a0 + 1 * pl, *p6 = au + 8 * pl, *p7 = ad + 5 * pl;
+    if (right_plain) {
+        stg4(p3, F[1][3], F[2][3], F[3][3], r3);
+        stg4(p6, F[1][6], F[2][6], F[3][6], r6);
+        stg4(p7, F[1][7], F[2][7], F[3][7], r7);
+    } else {
+        p3[0] = F[1][3]; p3[1] = F[2][3]; p3[2] = F[3][3];
+        p6[0] = F[1][6]; p6[1] = F[2][6]; p6[2] = F[3][6];
+        p7[0] = F[1][7]; p7[1] = F[2][7]; p7[2] = F[3][7];
     }
-    if (MACRO && in_row) {
+    if (!left_plain) { p3[lo] = F[0][3]; p6[lo] = F[0][6]; p7[lo] = F[0][7]; }
+    if (MACRO) {
         const float one[4] = {1.0f, 1.0f, 1.0f, 1.0f};
         if ((nx & 3) == 0) store_macro4<true>(P, (size_t)l * nx + x0, mux, muy, mrho, one);
         else store_macro4<false>(P, (size_t)l * nx + x0, mux, muy, mrho, one);

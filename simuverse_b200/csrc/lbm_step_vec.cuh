@@ -29,6 +29,8 @@
 
 #include <unistd.h>
 
+#include <algorithm>
+
 #include "lbm_device.cuh"
 
 namespace lbm {
@@ -47,7 +49,17 @@ struct StepSync {
     unsigned int step_no;         // steps completed by this slab before the current one
 };
 
-constexpr int kVecThreads = 128;                 // 4 warps, 512 cells of one row per CTA
+// Compile-time tuning knobs (defaults = the measured best; profiles/ has the sweep)
+#ifndef LBM_VEC_THREADS
+#define LBM_VEC_THREADS 128
+#endif
+#ifndef LBM_LOAD_HINT   // 0: ld.global.nc (read-only path)  1: + L1::no_allocate  2: plain ld.global
+#define LBM_LOAD_HINT 0
+#endif
+#ifndef LBM_STORE_HINT  // 0: st.global  1: st.global.cs (streaming)  2: st.global.wt
+#define LBM_STORE_HINT 0
+#endif
+constexpr int kVecThreads = LBM_VEC_THREADS;     // 4 warps, 512 cells of one row per CTA
 constexpr int kCellsPerCta = kVecThreads * 4;
 constexpr long long kWaitTimeoutNs = 4000000000ll;  // 4 s: never hang the GPU on a lost neighbour
 
@@ -100,9 +112,25 @@ __device__ __forceinline__ void signal_neighbours(const StepSync &S, unsigned in
     }
 }
 
-__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ldg4(const float *p) {
+#if LBM_LOAD_HINT == 1
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#elif LBM_LOAD_HINT == 2
+    return *reinterpret_cast<const float4 *>(p);
+#else
+    return __ldg(reinterpret_cast<const float4 *>(p));
+#endif
+}
 __device__ __forceinline__ void stg4(float *p, float a, float b, float c, float d) {
+#if LBM_STORE_HINT == 1
+    __stcs(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+#elif LBM_STORE_HINT == 2
+    __stwt(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
+#else
     *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+#endif
 }
 
 // Shift towards +x: cell x takes the value of x-1.  `edge` is the element left of the lane's
@@ -214,10 +242,9 @@ __device__ __forceinline__ void store_macro4(const SlabParams &P, size_t c, cons
 // here (best when mixed warps are rare: no second launch); otherwise mixed warps are skipped and
 // k_step_mixed processes them.
 template <bool MACRO, bool INLINE_MIXED>
-__global__ void __launch_bounds__(kVecThreads) k_step_vec(const __grid_constant__ SlabParams P,
-                                                          const __grid_constant__ StepSync S, int rb, int tiles_x) {
-    const int row_k = blockIdx.x / tiles_x;
-    const int tile = blockIdx.x - row_k * tiles_x;
+__device__ __forceinline__ void step_vec_block(const SlabParams &P, const StepSync &S, int rb, int tiles_x, unsigned int bid) {
+    const int row_k = bid / tiles_x;
+    const int tile = bid - row_k * tiles_x;
     const int x0 = (tile * kVecThreads + threadIdx.x) * 4;
 
     if (row_k < 2) {
@@ -267,6 +294,22 @@ __global__ void __launch_bounds__(kVecThreads) k_step_vec(const __grid_constant_
         if ((nx & 3) == 0) store_macro4<true>(P, (size_t)l * nx + x0, mux, muy, mrho, one);
         else store_macro4<false>(P, (size_t)l * nx + x0, mux, muy, mrho, one);
     }
+}
+
+#ifndef LBM_PERSISTENT_CTAS_PER_SM
+#define LBM_PERSISTENT_CTAS_PER_SM 0   // 0: one CTA per 512-cell tile;  n: n CTAs per SM striding over the tiles
+#endif
+
+template <bool MACRO, bool INLINE_MIXED>
+__global__ void __launch_bounds__(kVecThreads) k_step_vec(const __grid_constant__ SlabParams P,
+                                                          const __grid_constant__ StepSync S, int rb, int tiles_x,
+                                                          unsigned int total_blocks) {
+#if LBM_PERSISTENT_CTAS_PER_SM > 0
+    for (unsigned int bid = blockIdx.x; bid < total_blocks; bid += gridDim.x)
+        step_vec_block<MACRO, INLINE_MIXED>(P, S, rb, tiles_x, bid);
+#else
+    step_vec_block<MACRO, INLINE_MIXED>(P, S, rb, tiles_x, blockIdx.x);
+#endif
 }
 
 // ------------------------------------------------------------------ mixed warps
@@ -402,13 +445,18 @@ inline cudaError_t launch_step_vec(const SlabParams &P, const StepSync &S, const
     const long long blocks = rows_k * tiles_x;
     if (blocks > 2147483647ll) return cudaErrorInvalidConfiguration;
     *launched = 1;
+    unsigned int grid = (unsigned int)blocks;
+#if LBM_PERSISTENT_CTAS_PER_SM > 0
+    grid = (unsigned int)std::min<long long>(blocks, 148ll * LBM_PERSISTENT_CTAS_PER_SM);
+#endif
+    const unsigned int total = (unsigned int)blocks;
     if (M.rare) {
-        if (macro) k_step_vec<true, true><<<(unsigned int)blocks, kVecThreads, 0, stream>>>(P, S, rb, tiles_x);
-        else k_step_vec<false, true><<<(unsigned int)blocks, kVecThreads, 0, stream>>>(P, S, rb, tiles_x);
+        if (macro) k_step_vec<true, true><<<grid, kVecThreads, 0, stream>>>(P, S, rb, tiles_x, total);
+        else k_step_vec<false, true><<<grid, kVecThreads, 0, stream>>>(P, S, rb, tiles_x, total);
         return cudaGetLastError();
     }
-    if (macro) k_step_vec<true, false><<<(unsigned int)blocks, kVecThreads, 0, stream>>>(P, S, rb, tiles_x);
-    else k_step_vec<false, false><<<(unsigned int)blocks, kVecThreads, 0, stream>>>(P, S, rb, tiles_x);
+    if (macro) k_step_vec<true, false><<<grid, kVecThreads, 0, stream>>>(P, S, rb, tiles_x, total);
+    else k_step_vec<false, false><<<grid, kVecThreads, 0, stream>>>(P, S, rb, tiles_x, total);
     const uint32_t n = M.everywhere ? M.total : M.count;
     if (n > 0) {
         const uint32_t *list = M.everywhere ? nullptr : M.list;
