@@ -197,6 +197,9 @@ class FluidSimulator {
         check(lbm_particles_update(node_.handle()), node_.handle());
     }
 
+    // fluid_simulator.rs:234-248: only the state-changing part of the present pass (canvas alpha fade)
+    void draw_by_rpass() { check(lbm_canvas_fade(node_.handle()), node_.handle()); }
+
   private:
     static std::pair<int32_t, int32_t> grid(std::pair<uint32_t, uint32_t> canvas, int32_t count) {
         int32_t a = 0, b = 0;

@@ -149,6 +149,9 @@ int lbm_particles_write(LbmSim *sim, const TrajectoryParticle *src, uint64_t cou
 int lbm_particles_update(LbmSim *sim);              /* particle_update.wgsl:55-88 */
 int lbm_particles_read(LbmSim *sim, TrajectoryParticle *dst, uint64_t count);
 int lbm_canvas_clear(LbmSim *sim);
+/* The in-place part of the canvas present pass run by FluidSimulator::draw_by_rpass
+ * (fluid_simulator.rs:247, present.wgsl:19-22,43-49): alpha fade of every lit pixel. */
+int lbm_canvas_fade(LbmSim *sim);
 int lbm_canvas_read(LbmSim *sim, Pixel *dst);       /* canvas_w*canvas_h pixels */
 
 /* ------------------------------------------------------------------ multi-GPU wiring */

@@ -502,6 +502,19 @@ void orc_particle_update(const LbmUniform *u, const FieldUniform *field, const P
     }
 }
 
+/* present.wgsl:19-22,43-49 */
+void orc_canvas_fade(const FieldUniform *field, const ParticleUniform *pu, Pixel *canvas) {
+    const size_t n = (size_t)field->canvas_size[0] * (size_t)field->canvas_size[1];
+    for (size_t i = 0; i < n; i++) {
+        Pixel p = canvas[i];
+        if (p.alpha > 0.001f) {
+            if (p.alpha >= 0.2f) p.alpha = p.alpha * pu->fade_out_factor;
+            else p.alpha = p.alpha * 0.5f;
+            canvas[i] = p;
+        }
+    }
+}
+
 /* ---------------------------------------------------------------- host mutations */
 
 /* d2q9_node.rs:215-245 */

@@ -77,6 +77,11 @@ int orc_step_n(const LbmUniform *u, int32_t nx, int32_t ny, float *buf0, float *
 void orc_particle_update(const LbmUniform *u, const FieldUniform *field, const ParticleUniform *pu,
                          TrajectoryParticle *particles, Pixel *canvas, const uint16_t *macro_f16);
 
+/* assets/wgsl/present.wgsl:19-22,43-49: the in-place part of the canvas present pass (what
+ * FluidSimulator::draw_by_rpass runs, fluid_simulator.rs:247): every pixel with alpha > 0.001 fades,
+ * alpha *= fade_out_factor when alpha >= 0.2, else alpha *= 0.5.  (The fragment colour is render-only.) */
+void orc_canvas_fade(const FieldUniform *field, const ParticleUniform *pu, Pixel *canvas);
+
 /* d2q9_node.rs:215-245 add_obstacle. Mutates the host mirror; writes the patch the
  * reference uploads (rows [y-28, y+28) x nx) to `patch` (capacity 56*nx) and its byte
  * offset into the info buffer. Returns the number of LatticeInfo elements in the patch. */

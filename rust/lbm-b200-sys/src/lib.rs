@@ -136,6 +136,7 @@ unsafe extern "C" {
     pub fn lbm_particles_update(sim: *mut LbmSim) -> c_int;
     pub fn lbm_particles_read(sim: *mut LbmSim, dst: *mut TrajectoryParticle, count: u64) -> c_int;
     pub fn lbm_canvas_clear(sim: *mut LbmSim) -> c_int;
+    pub fn lbm_canvas_fade(sim: *mut LbmSim) -> c_int;
     pub fn lbm_canvas_read(sim: *mut LbmSim, dst: *mut Pixel) -> c_int;
 
     pub fn lbm_ipc_export(sim: *mut LbmSim, out: *mut LbmIpcBlob) -> c_int;

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "lbm_particles_update": (C.c_int, [_H]),
     "lbm_particles_read": (C.c_int, [_H, _vp, _u64]),
     "lbm_canvas_clear": (C.c_int, [_H]),
+    "lbm_canvas_fade": (C.c_int, [_H]),
     "lbm_canvas_read": (C.c_int, [_H, _vp]),
     "lbm_ipc_export": (C.c_int, [_H, C.POINTER(LbmIpcBlob)]),
     "lbm_ipc_attach": (C.c_int, [_H, C.POINTER(LbmIpcBlob), C.POINTER(LbmIpcBlob)]),

@@ -784,6 +784,15 @@ extern "C" int lbm_canvas_clear(LbmSim *s) {
     return LBM_OK;
 }
 
+extern "C" int lbm_canvas_fade(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->canvas) return fail(s, LBM_ERR_STATE, "handle was created with max_particles = 0");
+    if (!s->have_pu) return fail(s, LBM_ERR_STATE, "lbm_write_particle_uniform has not been called");
+    CU(cudaSetDevice(s->device));
+    k_canvas_fade<<<148 * 8, 256, 0, s->stream>>>(s->canvas, (size_t)s->canvas_w * s->canvas_h, s->pu.fade_out_factor);
+    return check_launch(s, "k_canvas_fade");
+}
+
 extern "C" int lbm_canvas_read(LbmSim *s, Pixel *dst) {
     if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
     if (!s->canvas) return fail(s, LBM_ERR_STATE, "handle was created with max_particles = 0");

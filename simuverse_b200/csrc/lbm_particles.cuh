@@ -81,6 +81,14 @@ __global__ void __launch_bounds__(256) k_particle_update(const __half *__restric
     particles[p_index] = p;
 }
 
+// present.wgsl:19-22,43-49 — the in-place fade of the canvas that the present pass performs
+__global__ void __launch_bounds__(256) k_canvas_fade(Pixel *canvas, size_t n, float fade_out_factor) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = canvas[i].alpha;
+        if (a > 0.001f) canvas[i].alpha = (a >= 0.2f) ? fmul(a, fade_out_factor) : fmul(a, 0.5f);
+    }
+}
+
 inline cudaError_t launch_particle_update(const SlabParams &P, const FieldUniform &field, const ParticleUniform &pu,
                                           TrajectoryParticle *particles, Pixel *canvas, cudaStream_t stream) {
     if (pu.num[0] <= 0 || pu.num[1] <= 0) return cudaSuccess;

@@ -280,6 +280,9 @@ class D2Q9Node:
     def canvas_clear(self):
         check(lib.lbm_canvas_clear(self._h), self._h)
 
+    def canvas_fade(self):
+        check(lib.lbm_canvas_fade(self._h), self._h)
+
     def read_canvas(self):
         out = np.empty(self.canvas_size[0] * self.canvas_size[1], dtype=PIXEL_DTYPE)
         check(lib.lbm_canvas_read(self._h, ptr(out)), self._h)

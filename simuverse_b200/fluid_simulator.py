@@ -98,6 +98,12 @@ class FluidSimulator:
         self.fluid_compute_node.reset_lattice_info()
         self.pre_pos = (0.0, 0.0)
 
+    def draw_by_rpass(self):
+        """fluid_simulator.rs:234-248 draws the canvas with present.wgsl; the part of that pass that changes
+        state — the in-place alpha fade of the canvas (present.wgsl:43-49) — is all that is reproduced."""
+        if self._particles:
+            self.fluid_compute_node.canvas_fade()
+
     def compute(self, n_frames=1):
         """fluid_simulator.rs:217-232: one frame = step(0), particles, step(1), particles."""
         self.fluid_compute_node.compute_frames(n_frames)

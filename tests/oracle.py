@@ -67,6 +67,7 @@ def lib():
         L.orc_step_n.argtypes = [C.POINTER(LbmUniform), i32, i32, vp, vp, vp, vp, vp, C.c_int, C.c_int]
         L.orc_particle_update.argtypes = [
             C.POINTER(LbmUniform), C.POINTER(FieldUniform), C.POINTER(ParticleUniform), vp, vp, vp]
+        L.orc_canvas_fade.argtypes = [C.POINTER(FieldUniform), C.POINTER(ParticleUniform), vp]
         L.orc_add_obstacle.restype = C.c_size_t
         L.orc_add_obstacle.argtypes = [i32, i32, vp, u32, u32, vp, C.POINTER(u64)]
         L.orc_on_click_guard.restype = C.c_int
@@ -159,6 +160,10 @@ class OracleSim:
     def particle_update(self, field, pu, particles, canvas):
         lib().orc_particle_update(C.byref(self.u), C.byref(field), C.byref(pu), ptr(particles),
                                   ptr(canvas) if canvas is not None else None, ptr(self.macro_f16))
+
+
+def canvas_fade(field, pu, canvas):
+    lib().orc_canvas_fade(C.byref(field), C.byref(pu), ptr(canvas))
 
 
 def add_obstacle(nx, ny, mirror, x, y):
