@@ -43,6 +43,17 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(config, overridden):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if not overridden and str(config) in t:
+            return t[str(config)]["bytes_per_launch"], t[str(config)]["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def workload_for(n_gpus, override, config=None):
     """(nx, ny, name, kind) of the BASELINE.json config being run. kind: 'steps' or 'frames'."""
     if config is None:
@@ -345,6 +356,7 @@ def main():
         peak, peak_src = measured_hbm_peak()
         per_launch_s = ms * 1e-3 / steps      # one k_step_vec launch per lattice update
         achieved = BYTES_PER_SITE * (sites / world) / per_launch_s / 1e9
+        traffic, traffic_src = measured_traffic(config, bool(args.lattice) or world > 1 or args.aa or args.generic)
         out = {
             "metric": METRIC, "value": value, "unit": "MLUPS", "n_gpus": args.gpus, "steps": steps,
             "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
@@ -358,7 +370,7 @@ def main():
             "clocks": clocks,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": BYTES_PER_SITE * sites // world,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "host_wall_ms_per_step": (t1 - t0) * 1e3 / steps,
