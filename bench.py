@@ -349,6 +349,33 @@ def main():
                            "each] + ")
                         + "lbm_read_macro(RGBA16F field of the slab -> pinned host memory); synchronous calls, "
                           "wall clock, max over ranks")}
+        # informational second flavour: the per-frame result read back is one scalar metric (the f64 total
+        # mass, like reading a loss) instead of the whole field — not PCIe-bound, but pays a reduction pass
+        import ctypes as C
+
+        mass_out = C.c_double()
+
+        def e2e_metric_step():
+            check(lib.lbm_write_lattice_info(node2._h, off, ptr(patch), patch.nbytes), node2._h)
+            check(lib.lbm_compute_frames(node2._h, 1), node2._h)
+            check(lib.lbm_total_mass(node2._h, lib.lbm_swap_index(node2._h), C.byref(mass_out)), node2._h)
+
+        for _ in range(3):
+            e2e_metric_step()
+        barrier(node2)
+        ta = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_metric_step()
+        barrier(node2)
+        dt2 = time.perf_counter() - ta
+        if dist is not None:
+            t = torch.tensor([dt2], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt2 = float(t.item())
+        e2e["metric_only_variant"] = {
+            "value": sites * per_call * args.e2e_steps / dt2 / 1e6, "unit": "MLUPS",
+            "h2d_bytes_per_step": int(patch.nbytes) * world // per_call, "d2h_bytes_per_step": 8 * world // per_call,
+            "what": "same host calls, but the result read back per frame is lbm_total_mass (one f64) instead of the field"}
         barrier(node2)
         node2.close()
 
