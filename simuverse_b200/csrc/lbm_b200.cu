@@ -612,6 +612,13 @@ extern "C" int lbm_sync(LbmSim *s) {
     if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    if (s->d.world > 1) {
+        // sticky word set by an edge CTA whose wait for a neighbour slab ran into the 4 s bound
+        unsigned int timed_out = 0;
+        CU(cudaMemcpy(&timed_out, s->sync.flags + 3, sizeof(timed_out), cudaMemcpyDeviceToHost));
+        if (timed_out)
+            return fail(s, LBM_ERR_STATE, "a step of slab %d gave up waiting for a neighbour slab (is every slab being stepped?); results are invalid", s->d.rank);
+    }
     return LBM_OK;
 }
 

@@ -252,3 +252,27 @@ def test_full_size_properties_8192_porous_and_16384():
         mx = [0.6] + [0.2222] * 4 + [0.1111] * 4
         for i in range(9):
             assert cur_a[i].min() >= 0.0 and cur_a[i].max() <= np.float32(mx[i])
+
+
+def test_lost_neighbour_times_out_instead_of_hanging(orc):
+    """A slab whose neighbour is never stepped must not hang the GPU: the edge CTAs give up after a
+    bounded wait and lbm_sync reports it."""
+    import time
+
+    from simuverse_b200.slabs import SlabGroup
+
+    nx, ny = 128, 64
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    grp = SlabGroup((nx * 2, ny * 2), setting(W.CUSTOM), lattice=(nx, ny), n_slabs=2, lattice_info=info)
+    a, b = grp.nodes
+    a.step_n(1)           # fine: neighbours' progress (0) is enough for the first update
+    a.sync()
+    t0 = time.time()
+    a.step_n(1)           # needs slab b's first update, which never comes
+    with pytest.raises(sb.LbmError) as e:
+        a.sync()
+    assert e.value.status == _capi.ERR_STATE and "neighbour" in str(e.value)
+    assert 2.0 < time.time() - t0 < 30.0
+    b.sync()
+    a.close()
+    b.close()
