@@ -375,3 +375,39 @@ def test_frame_loop_with_particles_matches_oracle(orc):
     assert same[hit_o].mean() > 0.97
     compare_state(fs.fluid_compute_node, sim, "after 60 frames")
     fs.fluid_compute_node.close()
+
+
+def test_slabs_mid_run_obstacle_and_force_across_a_cut(orc):
+    """Interactive mutation path on a decomposed lattice: an add_obstacle disc and transient
+    force cells that straddle a slab cut are handed to every slab (each keeps its rows + halo rows)."""
+    nx, ny, n_slabs = 320, 240, 3
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    s = setting(W.POISEUILLE)
+    one = sb.D2Q9Node((nx * 2, ny * 2), s, lattice=(nx, ny), lattice_info=info)
+    grp = SlabGroup((nx * 2, ny * 2), s, lattice=(nx, ny), n_slabs=n_slabs, lattice_info=info)
+    sim = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 0, nx * ny), threads=4)
+    for t in (one, grp):
+        t.step_n(25)
+    sim.step(25)
+    mirror = info.copy()
+    off, patch = orc.add_obstacle(nx, ny, mirror, 200, 80)      # disc centred on the cut at y = 80
+    offs, cells = orc.add_external_force(nx, ny, 2, (300.0, 330.0), (240.0, 300.0))  # crosses the cut at y = 160
+    assert len(offs) > 10 and {int(o) // 16 // nx for o in offs} >= {159, 160}
+    writes = [(off, patch)] + [(int(o), np.array([c], W.LATTICE_INFO_DTYPE)) for o, c in zip(offs, cells)]
+    for o, c in writes:
+        one.write_lattice_info(o, c)
+        grp.write_lattice_info(o, c)
+        sim.write_lattice_info(o, c)
+    new_solid = (mirror["material"] == 4).reshape(ny, nx) & (info["material"] != 4).reshape(ny, nx)
+    live = ~new_solid
+    for k in (1, 1, 48, 45):  # runs past the 90-step countdown of the force cells
+        one.step_n(k)
+        grp.step_n(k)
+        sim.step(k)
+        want = sim.distributions(sim.swap)
+        assert_bits_equal(one.read_distributions(sim.swap)[:, live], want[:, live], f"+{k} one slab")
+        assert_bits_equal(grp.read_distributions(sim.swap)[:, live], want[:, live], f"+{k} {n_slabs} slabs")
+        assert grp.read_lattice_info().tobytes() == sim.info.tobytes()
+    assert_bits_equal(grp.read_macro(), sim.macro(), "macro")
+    one.close()
+    grp.close()
