@@ -2,7 +2,8 @@
  * lbm_oracle.c — CPU restatement of the reference's D2Q9 LBM path (see lbm_oracle.h).
  *
  * TEST INFRASTRUCTURE ONLY — never linked into, loaded by, or called from the product.
- * PARITY UNPINNED (no reference golden vectors exist; see header).
+ * Pinned to the reference's WGSL source executed by tests/wgsl_ref (see lbm_oracle.h); the Rust host
+ * helpers restated here remain unpinned by execution.
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math [-fopenmp]  (oracle/Makefile).
  * Every expression is written in the reference's source order so that, with FMA

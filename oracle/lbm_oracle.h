@@ -5,14 +5,22 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may build, load or call it, and only as the checker / reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (Rust + WGSL on wgpu) has no tests, golden vectors
- * or fixtures for this path and cannot be built or run here (no
- * cargo/rustc, no Vulkan ICD).  This file restates the reference's own in-tree
- * arithmetic — the WGSL shaders and the Rust host functions cited per function —
- * in plain C, f32, round-to-nearest, no FMA contraction (-ffp-contract=off),
- * evaluated in WGSL source order.  It is cross-checked against an independent numpy
- * restatement (tests/np_restatement.py) and against the derived known-answer values
- * listed in SURVEY.md §8c.
+ * HOW IT IS PINNED: the reference (Rust + WGSL on wgpu) has no tests, golden vectors or fixtures
+ * for this path and cannot be built or run through wgpu here (no cargo/rustc,
+ * no Vulkan ICD).  What CAN be executed is the reference's own shader text: tests/wgsl_ref
+ * transpiles the unmodified assets/wgsl/lbm/{init,collide_stream,boundary,particle_update}.wgsl
+ * (after the reference's #include expansion) to Python and evaluates them with IEEE f32 scalars;
+ * tests/golden/make_wgsl_golden.py commits the resulting vectors (tests/golden/wgsl_*.npz) and
+ * tests/test_oracle.py requires this oracle to reproduce them bit for bit (distributions, macro
+ * texture, LatticeInfo, particles, canvas).  Not pinned by execution: the Rust HOST helpers
+ * (LbmUniform::new, init_lattice_material, add_obstacle, add_external_force, particle seeding),
+ * which are restated from source and checked only against the derived known answers of
+ * SURVEY.md §8c — "parity unpinned" still applies to those.
+ *
+ * This file restates the reference's in-tree arithmetic — the WGSL shaders and the Rust host
+ * functions cited per function — in plain C, f32, round-to-nearest, no FMA contraction
+ * (-ffp-contract=off), evaluated in WGSL source order.  It is additionally cross-checked against
+ * an independent numpy restatement (tests/np_restatement.py).
  */
 #ifndef LBM_ORACLE_H
 #define LBM_ORACLE_H

@@ -8,7 +8,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_cases():
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Vectors made by the independent numpy restatement (tests/golden/make_golden.py)."""
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("wgsl_"))
+
+
+def wgsl_golden_cases():
+    """Vectors made by executing the reference's own WGSL source (tests/golden/make_wgsl_golden.py)."""
+    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "wgsl_*.npz")))
 
 
 def bits(a):

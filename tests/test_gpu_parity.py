@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import simuverse_b200 as sb
-from helpers import assert_bits_equal, assert_close_rel, golden_cases, tau_default
+from helpers import assert_bits_equal, assert_close_rel, golden_cases, tau_default, wgsl_golden_cases
 from simuverse_b200 import wire as W
 from simuverse_b200.slabs import SlabGroup
 
@@ -411,3 +411,47 @@ def test_slabs_mid_run_obstacle_and_force_across_a_cut(orc):
     assert_bits_equal(grp.read_macro(), sim.macro(), "macro")
     one.close()
     grp.close()
+
+
+# ------------------------------------------------------------------ pinned to the reference's WGSL source
+
+@pytest.mark.parametrize("flags", [0, sb.FLAG_KERNEL_GENERIC, sb.FLAG_AA])
+@pytest.mark.parametrize("path", wgsl_golden_cases())
+def test_cuda_matches_executed_reference_wgsl(path, flags):
+    """Golden vectors produced by running the reference's own WGSL shader text
+    (tests/golden/make_wgsl_golden.py): the CUDA path must reproduce them bit for bit."""
+    g = np.load(path)
+    nx, ny, steps = int(g["nx"]), int(g["ny"]), int(g["steps"])
+    preset = W.LID_DRIVEN_CAVITY if int(g["fluid_ty"]) == 1 else W.CUSTOM  # only selects fluid_ty
+    s = setting(preset)
+    with_particles = "particles" in g.files
+    if with_particles:
+        if flags == sb.FLAG_KERNEL_GENERIC:
+            pytest.skip("one particle run per storage scheme is enough")
+        num = tuple(int(v) for v in g["particle_num"])
+        fs = sb.FluidSimulator((nx * 2, ny * 2), s, particles=True, lattice=(nx, ny), lattice_info=g["info"], flags=flags)
+        node = fs.fluid_compute_node
+        pu = s.particles_uniform_data
+        pu.num[:] = list(num)
+        node.write_particle_uniform(pu)
+        node.write_particles(g["particles_init"])
+        fs.compute(steps // 2)
+        assert node.read_particles(num[0] * num[1]).tobytes() == g["particles"].tobytes(), "particle trajectories"
+        cg = node.read_canvas().reshape(-1)
+        assert ((cg["alpha"] != 0) == (g["canvas"]["alpha"] != 0)).all()
+        same = (cg["velocity_x"] == g["canvas"]["velocity_x"]) & (cg["alpha"] == g["canvas"]["alpha"])
+        assert same.mean() > 0.999  # pixels hit by several particles in one pass race in the reference as well
+        np.testing.assert_array_equal(node.read_macro_tex().view(np.uint16), g["macro_f16"])
+    else:
+        node = sb.D2Q9Node((nx * 2, ny * 2), s, lattice=(nx, ny), lattice_info=g["info"],
+                           flags=flags | sb.FLAG_MACRO_EVERY_STEP)
+        for off, cell in zip(g["post_offsets"], g["post_cells"]):
+            node.write_lattice_info(int(off), np.array([cell], W.LATTICE_INFO_DTYPE))
+        node.step_n(steps)
+        np.testing.assert_array_equal(node.read_macro_tex().view(np.uint16), g["macro_f16"])
+    assert node.swap_index == int(g["swap"])
+    assert_bits_equal(node.read_distributions(node.swap_index), g["buf_cur"], "current buffer")
+    if not flags & sb.FLAG_AA:
+        assert_bits_equal(node.read_distributions(1 - node.swap_index), g["buf_prev"], "previous buffer")
+    assert node.read_lattice_info().tobytes() == g["info_after"].tobytes()
+    node.close()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import np_restatement as R
-from helpers import assert_bits_equal, golden_cases, tau_default
+from helpers import assert_bits_equal, golden_cases, tau_default, wgsl_golden_cases
 from simuverse_b200 import wire as W
 
 
@@ -221,3 +221,67 @@ def test_mass_drifts_like_the_reference(orc):
     s.step(400)
     drift = (s.total_mass() - m0) / m0
     assert -5e-2 < drift < -1e-5
+
+
+# ------------------------------------------------------------------ pinned to the reference's WGSL source
+
+@pytest.mark.parametrize("path", wgsl_golden_cases())
+def test_oracle_matches_executed_reference_wgsl(orc, path):
+    """The golden vectors come from the reference's own shader text, transpiled and executed
+    (tests/golden/make_wgsl_golden.py): init, collide_stream, boundary and particle_update."""
+    g = np.load(path)
+    nx, ny, steps = int(g["nx"]), int(g["ny"]), int(g["steps"])
+    u = orc.uniform_new(tau_default(), int(g["fluid_ty"]), nx * ny)
+    s = orc.OracleSim(nx, ny, g["info"], u)
+    for off, cell in zip(g["post_offsets"], g["post_cells"]):
+        s.write_lattice_info(int(off), np.array([cell], W.LATTICE_INFO_DTYPE))
+    if "particles" in g.files:
+        num = tuple(int(v) for v in g["particle_num"])
+        canvas_size = (nx * 2, ny * 2)
+        from simuverse_b200.d2q9_node import SettingObj
+
+        pu = SettingObj().particles_uniform_data
+        pu.num[:] = list(num)
+        parts = orc.init_trajectory_particles(canvas_size[0], canvas_size[1], num[0], num[1], pu.life_time, 0x5EED)
+        assert parts.tobytes() == g["particles_init"].tobytes()
+        canvas = np.zeros(canvas_size[0] * canvas_size[1], W.PIXEL_DTYPE)
+        field = orc.field_uniform_new(nx, ny, 2, *canvas_size)
+        for _ in range(steps):
+            s.step(1)
+            s.particle_update(field, pu, parts, canvas)
+        assert parts.tobytes() == g["particles"].tobytes(), "particle trajectories"
+        assert canvas.tobytes() == g["canvas"].tobytes(), "canvas"
+    else:
+        s.step(steps)
+    assert s.swap == int(g["swap"])
+    assert_bits_equal(s.distributions(s.swap), g["buf_cur"], "current buffer")
+    assert_bits_equal(s.distributions(1 - s.swap), g["buf_prev"], "previous buffer")
+    np.testing.assert_array_equal(s.macro_f16, g["macro_f16"].reshape(-1))
+    assert s.info.tobytes() == g["info_after"].tobytes()
+
+
+def test_oracle_matches_reference_wgsl_live(orc):
+    """When the reference tree is present (build container), transpile and run its shaders right here."""
+    from wgsl_ref import harness as H
+
+    if not H.available():
+        pytest.skip("/root/reference is not present on this box")
+    nx, ny = 14, 11
+    info = orc.init_lattice_material(nx, ny, W.CUSTOM)
+    g = info.reshape(ny, nx)
+    g[5, 6] = (W.EXTERNAL_FORCE, -1, 0.05, -0.02)
+    g["material"][3:5, 9:11] = W.OBSTACLE
+    for fluid_ty in (0, 1):
+        u = orc.uniform_new(tau_default(), fluid_ty, nx * ny)
+        w = H.WgslLbm(nx, ny, info, u)
+        s = orc.OracleSim(nx, ny, info, u)
+        cell = np.array([(W.EXTERNAL_FORCE, 2, 0.03, 0.04)], W.LATTICE_INFO_DTYPE)
+        w.info[3 * nx + 3] = cell[0]
+        s.write_lattice_info((3 * nx + 3) * 16, cell)
+        for _ in range(4):
+            w.step(1)
+            s.step(1)
+            for b in (0, 1):
+                assert_bits_equal(w.buf[b], s.buf[b], f"fluid_ty {fluid_ty} buf{b}")
+            np.testing.assert_array_equal(w.macro.view(np.uint16).reshape(-1), s.macro_f16)
+            assert w.info.tobytes() == s.info.tobytes()

@@ -1,0 +1,212 @@
+"""Runtime for the Python emitted by wgsl2py: IEEE f32 scalars (numpy.float32, one rounding per
+operation), i32 as Python ints, WGSL value semantics for vectors / structs / arrays."""
+import numpy as np
+
+F = np.float32
+
+
+def f32(v):
+    return F(v)
+
+
+def i32(v):
+    """WGSL f32 -> i32 conversion: truncate toward zero (saturating)."""
+    if isinstance(v, (int, np.integer)):
+        return int(v)
+    if isinstance(v, Vec):
+        return Vec([i32(c) for c in v.v])
+    x = float(v)
+    if x != x:
+        return 0
+    return int(max(min(x, 2147483647.0), -2147483648.0))
+
+
+def u32(v):
+    return i32(v) & 0xFFFFFFFF if not isinstance(v, Vec) else Vec([u32(c) for c in v.v])
+
+
+_SWZ = {"x": 0, "y": 1, "z": 2, "w": 3, "r": 0, "g": 1, "b": 2, "a": 3}
+
+
+class Vec:
+    __slots__ = ("v",)
+    __array_ufunc__ = None  # numpy scalars must defer to Vec.__rmul__ etc.
+
+    def __init__(self, comps):
+        object.__setattr__(self, "v", list(comps))
+
+    def __getattr__(self, name):
+        idx = [_SWZ[c] for c in name]
+        return self.v[idx[0]] if len(idx) == 1 else Vec([self.v[i] for i in idx])
+
+    def __setattr__(self, name, value):
+        idx = [_SWZ[c] for c in name]
+        if len(idx) == 1:
+            self.v[idx[0]] = value
+        else:
+            for i, c in zip(idx, value.v):
+                self.v[i] = c
+
+    def __getitem__(self, i):
+        return self.v[i]
+
+    def __setitem__(self, i, val):
+        self.v[i] = val
+
+    def _bin(self, o, fn, swap=False):
+        ov = o.v if isinstance(o, Vec) else [o] * len(self.v)
+        return Vec([fn(b, a) if swap else fn(a, b) for a, b in zip(self.v, ov)])
+
+    def __add__(self, o): return self._bin(o, lambda a, b: a + b)
+    def __radd__(self, o): return self._bin(o, lambda a, b: a + b, True)
+    def __sub__(self, o): return self._bin(o, lambda a, b: a - b)
+    def __rsub__(self, o): return self._bin(o, lambda a, b: a - b, True)
+    def __mul__(self, o): return self._bin(o, lambda a, b: a * b)
+    def __rmul__(self, o): return self._bin(o, lambda a, b: a * b, True)
+    def __neg__(self): return Vec([-a for a in self.v])
+    def __eq__(self, o): return all(a == b for a, b in zip(self.v, o.v))
+    def __repr__(self): return f"Vec({self.v})"
+
+
+def vec(n, elem, args):
+    """vecN<elem>(...) constructor: scalars and vectors are flattened, one scalar is splatted."""
+    flat = []
+    for a in args:
+        flat.extend(a.v if isinstance(a, Vec) else [a])
+    if len(flat) == 1:
+        flat = flat * n
+    assert len(flat) == n, (n, flat)
+    conv = {"f32": f32, "i32": i32, "u32": u32}[elem]
+    return Vec([conv(c) for c in flat])
+
+
+def div(a, b):
+    if isinstance(a, Vec) or isinstance(b, Vec):
+        av = a.v if isinstance(a, Vec) else [a] * len(b.v)
+        bv = b.v if isinstance(b, Vec) else [b] * len(av)
+        return Vec([div(x, y) for x, y in zip(av, bv)])
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        q = abs(int(a)) // abs(int(b))  # WGSL integer division truncates toward zero
+        return q if (a >= 0) == (b >= 0) else -q
+    with np.errstate(all="ignore"):
+        return F(a) / F(b)
+
+
+def mod(a, b):
+    if isinstance(a, (int, np.integer)) and isinstance(b, (int, np.integer)):
+        return int(a) - int(b) * div(a, b)
+    return F(np.fmod(F(a), F(b)))
+
+
+def copy(v):
+    if isinstance(v, Vec):
+        return Vec(v.v)
+    if isinstance(v, list):
+        return [copy(x) for x in v]
+    if hasattr(v, "_wgsl_copy"):
+        return v._wgsl_copy()
+    return v
+
+
+def make_struct(name, fields, zeros):
+    class S:
+        __slots__ = tuple(fields)
+
+        def __init__(self, *args, **kw):
+            init = zeros()
+            for f, a in zip(fields, args):
+                init[f] = a
+            init.update(kw)
+            for f in fields:
+                object.__setattr__(self, f, copy(init[f]))
+
+        def _wgsl_copy(self):
+            return S(*[getattr(self, f) for f in fields])
+
+        def __repr__(self):
+            return name + "(" + ", ".join(f"{f}={getattr(self, f)!r}" for f in fields) + ")"
+
+    S.__name__ = name
+    return S
+
+
+# ---------------------------------------------------------------- builtins
+def dot(a, b):
+    s = a.v[0] * b.v[0]
+    for x, y in zip(a.v[1:], b.v[1:]):
+        s = s + x * y
+    return s
+
+
+def _map(fn, *xs):
+    if any(isinstance(x, Vec) for x in xs):
+        n = len(next(x for x in xs if isinstance(x, Vec)).v)
+        cols = [x.v if isinstance(x, Vec) else [x] * n for x in xs]
+        return Vec([fn(*c) for c in zip(*cols)])
+    return fn(*xs)
+
+
+def clamp(x, lo, hi):
+    return _map(lambda a, b, c: min(max(a, b), c) if isinstance(a, (int, np.integer)) else F(min(max(a, F(b)), F(c))), x, lo, hi)
+
+
+def floor(x): return _map(lambda a: F(np.floor(a)), x)
+def ceil(x): return _map(lambda a: F(np.ceil(a)), x)
+def abs(x): return _map(lambda a: a.__abs__() if isinstance(a, (int, np.integer)) else F(np.abs(a)), x)  # noqa: A001
+def sqrt(x): return _map(lambda a: F(np.sqrt(a)), x)
+
+
+def min(a, b):  # noqa: A001
+    import builtins
+    return _map(lambda x, y: builtins.min(x, y), a, b)
+
+
+def max(a, b):  # noqa: A001
+    import builtins
+    return _map(lambda x, y: builtins.max(x, y), a, b)
+
+
+def length(v): return F(np.sqrt(dot(v, v)))
+
+
+def smoothstep(lo, hi, x):
+    t = clamp(div(x - lo, hi - lo), F(0), F(1))
+    return t * t * (F(3) - F(2) * t)
+
+
+class StorageF32:
+    """``struct StoreFloat { data: array<f32> }`` bound to a numpy float32 array."""
+
+    def __init__(self, arr):
+        self.data = arr
+
+
+class StructArray:
+    """``array<SomeStruct>`` over a numpy structured array; reads copy out, writes copy in."""
+
+    def __init__(self, arr, cls, to_struct, from_struct):
+        self.arr, self.cls, self.to_struct, self.from_struct = arr, cls, to_struct, from_struct
+
+    def __getitem__(self, i):
+        return self.to_struct(self.cls, self.arr[i])
+
+    def __setitem__(self, i, s):
+        self.from_struct(self.arr, i, s)
+
+
+class Texture16F:
+    """rgba16float texture (storage write and sampled read): array of shape (ny, nx, 4) float16."""
+
+    def __init__(self, arr):
+        self.arr = arr
+
+
+def textureStore(tex, uv, value):
+    x, y = int(uv.v[0]), int(uv.v[1])
+    with np.errstate(over="ignore"):
+        tex.arr[y, x, :] = np.array([F(c) for c in value.v], np.float32).astype(np.float16)
+
+
+def textureLoad(tex, uv, level):
+    x, y = int(uv.v[0]), int(uv.v[1])
+    return Vec([F(c) for c in tex.arr[y, x, :].astype(np.float32)])
