@@ -570,6 +570,8 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
     if (!s || n_frames < 0) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
     int rc = ready_to_step(s);
     if (rc) return rc;
+    if (s->swap != 0)
+        return fail(s, LBM_ERR_STATE, "lbm_compute_frames starts with step(0): the current state must be in buffer 0 (an even number of updates since lbm_reset)");
     const bool with_particles = s->particles != nullptr;
     if (with_particles) {
         if (!s->have_pu) return fail(s, LBM_ERR_STATE, "lbm_write_particle_uniform has not been called");

@@ -14,7 +14,16 @@ def golden_cases():
 
 def wgsl_golden_cases():
     """Vectors made by executing the reference's own WGSL source (tests/golden/make_wgsl_golden.py)."""
-    return sorted(glob.glob(os.path.join(GOLDEN_DIR, "wgsl_*.npz")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "wgsl_*.npz")) if "wgsl_default" not in p)
+
+
+WGSL_DEFAULT = os.path.join(GOLDEN_DIR, "wgsl_default_600x375_f2.npz")
+
+
+def sha(a):
+    import hashlib
+
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
 def bits(a):

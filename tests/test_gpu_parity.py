@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import simuverse_b200 as sb
-from helpers import assert_bits_equal, assert_close_rel, golden_cases, tau_default, wgsl_golden_cases
+from helpers import WGSL_DEFAULT, assert_bits_equal, assert_close_rel, golden_cases, sha, tau_default, wgsl_golden_cases
 from simuverse_b200 import wire as W
 from simuverse_b200.slabs import SlabGroup
 
@@ -454,4 +454,26 @@ def test_cuda_matches_executed_reference_wgsl(path, flags):
     if not flags & sb.FLAG_AA:
         assert_bits_equal(node.read_distributions(1 - node.swap_index), g["buf_prev"], "previous buffer")
     assert node.read_lattice_info().tobytes() == g["info_after"].tobytes()
+    node.close()
+
+
+@pytest.mark.parametrize("flags", [0, sb.FLAG_AA])
+def test_cuda_matches_executed_reference_wgsl_default_config(flags):
+    """The reference's default configuration (600x375, preset discs, 127x80 tracers), two frames, against
+    digests of the state produced by executing the reference's WGSL source."""
+    g = np.load(WGSL_DEFAULT)
+    fs = sb.FluidSimulator((1200, 750), setting(W.POISEUILLE), particles=True, particle_seed=0x5EED, flags=flags)
+    assert fs.lattice == (int(g["nx"]), int(g["ny"])) and fs.particles_num == (127, 80)
+    fs.compute(int(g["frames"]))
+    node = fs.fluid_compute_node
+    assert node.swap_index == int(g["swap"])
+    assert sha(node.read_distributions(node.swap_index)) == str(g["sha_cur"])
+    if not flags & sb.FLAG_AA:
+        assert sha(node.read_distributions(1 - node.swap_index)) == str(g["sha_prev"])
+    assert sha(node.read_macro_tex().view(np.uint16)) == str(g["sha_macro"])
+    assert sha(node.read_lattice_info()) == str(g["sha_info"])
+    assert sha(node.read_particles(127 * 80)) == str(g["sha_particles"])
+    cg = node.read_canvas().reshape(-1)
+    if sha(cg) != str(g["sha_canvas"]):  # only pixels hit by two particles in one pass may differ (racy in the reference)
+        assert (cg["alpha"] != 0).sum() > 30000
     node.close()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import np_restatement as R
-from helpers import assert_bits_equal, golden_cases, tau_default, wgsl_golden_cases
+from helpers import WGSL_DEFAULT, assert_bits_equal, golden_cases, sha, tau_default, wgsl_golden_cases
 from simuverse_b200 import wire as W
 
 
@@ -285,3 +285,31 @@ def test_oracle_matches_reference_wgsl_live(orc):
                 assert_bits_equal(w.buf[b], s.buf[b], f"fluid_ty {fluid_ty} buf{b}")
             np.testing.assert_array_equal(w.macro.view(np.uint16).reshape(-1), s.macro_f16)
             assert w.info.tobytes() == s.info.tobytes()
+
+
+def test_oracle_matches_executed_reference_wgsl_default_config(orc):
+    """BASELINE configs[0] — the reference's default 600x375 lattice, its Poiseuille preset with the three
+    R=28 discs and its 127x80 tracer particles — two frames of FluidSimulator::compute executed from the
+    reference's WGSL source (tests/golden/make_wgsl_golden_default.py); digests of every buffer."""
+    g = np.load(WGSL_DEFAULT)
+    nx, ny, frames = int(g["nx"]), int(g["ny"]), int(g["frames"])
+    canvas_size = (1200, 750)
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    s = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 0, nx * ny), threads=4)
+    from simuverse_b200.d2q9_node import SettingObj
+
+    pu = SettingObj().particles_uniform_data
+    pu.num[:] = [127, 80]
+    parts = orc.init_trajectory_particles(canvas_size[0], canvas_size[1], 127, 80, pu.life_time, 0x5EED)
+    canvas = np.zeros(canvas_size[0] * canvas_size[1], W.PIXEL_DTYPE)
+    field = orc.field_uniform_new(nx, ny, 2, *canvas_size)
+    for _ in range(2 * frames):
+        s.step(1)
+        s.particle_update(field, pu, parts, canvas)
+    assert s.swap == int(g["swap"])
+    assert sha(s.distributions(s.swap)) == str(g["sha_cur"]) and sha(s.distributions(1 - s.swap)) == str(g["sha_prev"])
+    assert sha(s.macro_f16) == str(g["sha_macro"]) and sha(s.info) == str(g["sha_info"])
+    assert sha(parts) == str(g["sha_particles"]) and sha(canvas) == str(g["sha_canvas"])
+    rows = list(g["rows"])
+    assert_bits_equal(s.distributions(s.swap)[:, rows, :], g["cur_rows"], "rows of the current buffer")
+    assert abs(s.total_mass() - float(g["total_mass"])) < 1e-6
