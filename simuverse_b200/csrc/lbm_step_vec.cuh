@@ -11,14 +11,17 @@
 //     rows are streamed straight into registers — no shared-memory staging is needed for
 //     reuse; the only on-chip exchange is the shuffle;
 //   * a 1-byte class plane, read as one 32-bit word per thread, tells whether the thread's four
-//     cells are plain interior fluid.  Warps in which every thread says yes are "pure" and are
-//     handled by k_step_vec (vector stores).  All other warps (walls, obstacles, cells that
-//     bounce into a solid neighbour, inlet / force cells, the ragged end of a row) are "mixed";
-//     a compact list of them is rebuilt whenever the mask changes (k_scan_mixed) and processed
-//     by k_step_mixed: same vector loads + shuffles, then a warp transpose through shared memory
-//     so that the per-cell 32-bit stores (own slots, bounce-back scatter, dead-slot zeros) are
-//     issued with consecutive lanes on consecutive cells, i.e. as whole 128-byte lines.  Keeping
-//     the two paths in separate kernels keeps the hot one at 72 registers;
+//     cells are plain interior fluid.  Warps in which every thread says yes are "pure" (vector
+//     stores).  All other warps (walls, obstacles, cells that bounce into a solid neighbour,
+//     inlet / force cells, the ragged end of a row) are "mixed"; k_scan_mixed counts and lists them
+//     whenever the mask changes, and launch_step_vec picks one of three regimes:
+//       - mixed warps rare (channel-type masks): ONE launch, k_step_vec<.., INLINE_MIXED=true>; the few
+//         non-plain threads take the generic per-cell path of lbm_device.cuh inline;
+//       - otherwise k_step_vec<.., false> handles the pure warps and k_step_mixed the listed ones (or
+//         every interior warp when most are mixed, e.g. porous media): same vector loads + shuffles,
+//         then a warp transpose through shared memory so that the per-cell 32-bit stores (own slots,
+//         bounce-back scatter, dead-slot zeros) are issued with consecutive lanes on consecutive
+//         cells, i.e. as whole 128-byte lines;
 //   * the first and last row of a slab are processed by the CTAs with the lowest block
 //     indices through the generic path: their y-neighbours live in the adjacent slab
 //     (another GPU's memory mapped over NVLink, or the periodic wrap when there is one
