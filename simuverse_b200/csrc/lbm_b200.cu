@@ -135,7 +135,8 @@ int derive_rows(LbmSim *s, int l0, int l1) {
         CU(cudaMemcpyAsync(&M.count, M.count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         M.everywhere = M.count > M.total / 2;
-        M.rare = M.count <= M.total / 8;
+        // few mixed warps, or a lattice so small that a second launch costs more than a few slow threads
+        M.rare = M.count <= M.total / 8 || M.total <= 8192;
     }
     invalidate_graphs(s); // launch geometry is baked into captured graphs
     return LBM_OK;

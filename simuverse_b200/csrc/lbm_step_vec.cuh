@@ -56,12 +56,16 @@ struct StepSync {
 #ifndef LBM_VEC_THREADS
 #define LBM_VEC_THREADS 128
 #endif
+#ifndef LBM_INLINE_MIXED_UNROLL  // unroll of the per-cell loop of non-plain threads (latency vs code size)
+#define LBM_INLINE_MIXED_UNROLL 1
+#endif
 #ifndef LBM_LOAD_HINT   // 0: ld.global.nc (read-only path)  1: + L1::no_allocate  2: plain ld.global
 #define LBM_LOAD_HINT 0
 #endif
 #ifndef LBM_STORE_HINT  // 0: st.global  1: st.global.cs (streaming)  2: st.global.wt
 #define LBM_STORE_HINT 0
 #endif
+constexpr int kInlineMixedUnroll = LBM_INLINE_MIXED_UNROLL;
 constexpr int kVecThreads = LBM_VEC_THREADS;     // 4 warps, 512 cells of one row per CTA
 constexpr int kCellsPerCta = kVecThreads * 4;
 constexpr long long kWaitTimeoutNs = 4000000000ll;  // 4 s: never hang the GPU on a lost neighbour
@@ -270,7 +274,7 @@ __device__ __forceinline__ void step_vec_block(const SlabParams &P, const StepSy
     if (INLINE_MIXED) {
         if (!in_row) return;
         if (q.cw != 0 || ragged) {
-#pragma unroll 1
+#pragma unroll kInlineMixedUnroll
             for (int c = 0; c < 4; c++)
                 if (x0 + c < nx) update_cell<0>(P, rb, x0 + c, l);
             return;
@@ -444,7 +448,8 @@ inline cudaError_t launch_step_vec(const SlabParams &P, const StepSync &S, const
     const int tiles_x = (P.nx + kCellsPerCta - 1) / kCellsPerCta;
     const bool macro = P.macro16 || P.macro32;
     // block rows: 0 -> row 0, 1 -> row h-1, k >= 2 -> row k-1 (edge rows are dispatched first)
-    const long long rows_k = (P.h >= 2 && !M.everywhere) ? P.h : 2;
+    // (only the two edge rows when k_step_mixed takes every interior warp)
+    const long long rows_k = (P.h >= 2 && (M.rare || !M.everywhere)) ? P.h : 2;
     const long long blocks = rows_k * tiles_x;
     if (blocks > 2147483647ll) return cudaErrorInvalidConfiguration;
     *launched = 1;

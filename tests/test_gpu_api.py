@@ -41,7 +41,8 @@ def striped_mask(orc, nx, ny, period, width=3):
 def test_launch_regimes_match_oracle(orc, period, regime):
     """<= 1/8 mixed warps: one inline launch; <= 1/2: pure kernel + list kernel; else mixed kernel over
     everything.  All three must leave identical buffers."""
-    nx, ny = 4096, 96  # 32 warps per row: ~3/32, ~9/32 and 32/32 of them mixed (+ the two wall-adjacent rows)
+    nx, ny = 4096, 384  # 32 warps per row: ~3/32, ~9/32 and 32/32 of them mixed; > 8192 interior warps, so the
+    # small-lattice rule (always inline) does not apply
     info = striped_mask(orc, nx, ny, period)
     node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.CUSTOM), lattice=(nx, ny), lattice_info=info)
     before = node.launch_count
