@@ -292,6 +292,14 @@ def main():
     sites = nx * ny
     value = sites * steps / (ms * 1e-3) / 1e6
     mass = slab.total_mass() if slab is not None else node.total_mass()
+    # fluid-only rate for masked lattices: non-solid sites from the owned rows' LatticeInfo
+    mat = node.read_lattice_info()["material"]
+    fluid_sites = int(((mat != W.BOUNDARY) & (mat != W.OBSTACLE)).sum())
+    del mat
+    if dist is not None:
+        t = torch.tensor([fluid_sites], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        fluid_sites = int(t.item())
     barrier(node)  # no slab may unmap memory a neighbour still reads
     node.close()
 
@@ -393,7 +401,8 @@ def main():
                        "cuda_graphs": not args.no_graph and world == 1,
                        "kernel": "k_step_generic" if args.generic else ("k_aa_pull/k_aa_local" if args.aa else "k_step_vec"),
                        "state": "AA in-place, one copy of the SoA planes" if args.aa else "A/B ping-pong SoA planes",
-                       "total_mass_after": mass},
+                       "total_mass_after": mass, "fluid_sites": fluid_sites,
+                       "mflups_fluid_only": value * fluid_sites / sites},
             "clocks": clocks,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
