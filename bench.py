@@ -398,7 +398,7 @@ def main():
             "scaling": "weak" if (world == 1 or config == 4) else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name, "baseline_config": config, "lattice": [nx, ny], "tau": 0.56,
                        "l2": "inputs_larger_than_l2" if sites * 72 / world > 2.6e8 else "lattice fits in L2 (the reference's own size)",
-                       "cuda_graphs": not args.no_graph and world == 1,
+                       "cuda_graphs": not args.no_graph,
                        "kernel": "k_step_generic" if args.generic else ("k_aa_pull/k_aa_local" if args.aa else "k_step_vec"),
                        "state": "AA in-place, one copy of the SoA planes" if args.aa else "A/B ping-pong SoA planes",
                        "total_mass_after": mass, "fluid_sites": fluid_sites,

@@ -197,7 +197,6 @@ int launch_step(LbmSim *s, int rb) {
         if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_step_vec / k_step_mixed failed: %s", cudaGetErrorString(e));
         s->launches += n;
     }
-    s->sync.step_no++;
     s->steps_since_reset++;
     return LBM_OK;
 }
@@ -225,7 +224,8 @@ void invalidate_graphs(LbmSim *s) {
     if (s->graph_frame) { cudaGraphExecDestroy(s->graph_frame); s->graph_frame = nullptr; }
 }
 
-bool graphs_enabled(const LbmSim *s) { return s->d.world == 1 && !(s->d.flags & LBM_FLAG_NO_GRAPH); }
+// (multi-slab launches are replayable too: the step counter the edge CTAs compare against lives on the device)
+bool graphs_enabled(const LbmSim *s) { return !(s->d.flags & LBM_FLAG_NO_GRAPH); }
 
 int launch_particles(LbmSim *s) {
     cudaError_t e = launch_particle_update(s->P, s->field, s->pu, s->particles, s->canvas, s->stream);
@@ -238,7 +238,6 @@ int launch_particles(LbmSim *s) {
 template <typename F>
 int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
     const uint64_t launches = s->launches, since = s->steps_since_reset;
-    const unsigned int step_no = s->sync.step_no;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = body();
     cudaGraph_t g = nullptr;
@@ -246,7 +245,6 @@ int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
     *kernels = s->launches - launches;
     s->launches = launches; // nothing ran yet
     s->steps_since_reset = since;
-    s->sync.step_no = step_no;
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, g, 0);
@@ -552,7 +550,6 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
             CU(cudaGraphLaunch(g, s->stream));
             s->launches += s->graph_steps_kernels[s->swap];
             s->steps_since_reset += kGraphSteps;
-            s->sync.step_no += kGraphSteps;
         }
     }
     for (int i = 0; i < left; i++) {
@@ -597,7 +594,6 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
             CU(cudaGraphLaunch(s->graph_frame, s->stream));
             s->launches += s->graph_frame_kernels;
             s->steps_since_reset += 2;
-            s->sync.step_no += 2;
         } else {
             rc = frame();
             if (rc) return rc;

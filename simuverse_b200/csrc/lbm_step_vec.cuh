@@ -45,11 +45,11 @@ inline long getpid_portable() { return (long)getpid(); }
 //   [1] same for the DOWN neighbour
 //   [2] edge-CTA arrival counter of the running step
 //   [3] sticky error word (1 = a wait timed out)
+//   [4] steps completed by this slab (device-side, so that launches can be replayed from CUDA graphs)
 struct StepSync {
     unsigned int *flags;          // own
     unsigned int *peer_flags[2];  // up / down neighbour's flag words (peer memory)
     int world;
-    unsigned int step_no;         // steps completed by this slab before the current one
 };
 
 // Compile-time tuning knobs (defaults = the measured best; profiles/ has the sweep)
@@ -89,8 +89,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 __device__ __forceinline__ void wait_neighbours(const StepSync &S) {
     if (S.world > 1) {
         if (threadIdx.x == 0) {
+            const unsigned int step_no = *(volatile unsigned int *)(S.flags + 4); // written by the previous launch
             const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys(S.flags + 0) < S.step_no || ld_acquire_sys(S.flags + 1) < S.step_no) {
+            while (ld_acquire_sys(S.flags + 0) < step_no || ld_acquire_sys(S.flags + 1) < step_no) {
                 if ((long long)(globaltimer_ns() - t0) > kWaitTimeoutNs) {
                     atomicExch(S.flags + 3, 1u);
                     break;
@@ -111,9 +112,11 @@ __device__ __forceinline__ void signal_neighbours(const StepSync &S, unsigned in
             const unsigned int arrived = atomicAdd(S.flags + 2, 1u) + 1u;
             if (arrived == n_edge_ctas) {
                 atomicExch(S.flags + 2, 0u);
+                const unsigned int done = *(volatile unsigned int *)(S.flags + 4) + 1u;
+                *(volatile unsigned int *)(S.flags + 4) = done; // read by this slab's next launch only
                 __threadfence_system();
-                st_release_sys(S.peer_flags[0] + 1, S.step_no + 1u); // I am my up neighbour's DOWN neighbour
-                st_release_sys(S.peer_flags[1] + 0, S.step_no + 1u); // and my down neighbour's UP neighbour
+                st_release_sys(S.peer_flags[0] + 1, done); // I am my up neighbour's DOWN neighbour
+                st_release_sys(S.peer_flags[1] + 0, done); // and my down neighbour's UP neighbour
             }
         }
     }
