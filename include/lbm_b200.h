@@ -137,6 +137,10 @@ int lbm_slab_rows(const LbmSim *sim, int32_t *y0, int32_t *rows);
 int lbm_read_distributions(LbmSim *sim, int32_t which, float *dst);
 int lbm_write_distributions(LbmSim *sim, int32_t which, const float *src);
 int lbm_read_macro(LbmSim *sim, int32_t format, void *dst);
+/* Pipelined variant for per-frame consumers (handle created with LBM_FLAG_MACRO_EVERY_STEP): enqueues the
+ * device-to-host copy of the RGBA16F texture on a separate stream and returns; later steps write a second
+ * texture meanwhile.  dst (pinned host memory) is complete after lbm_sync. */
+int lbm_read_macro_async(LbmSim *sim, void *dst);
 /* Owned rows of the info buffer including device-side block_iter/material mutation
  * (collide_stream.wgsl:55-62). dst: rows*nx LatticeInfo. */
 int lbm_read_lattice_info(LbmSim *sim, LatticeInfo *dst);

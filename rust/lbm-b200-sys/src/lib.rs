@@ -128,6 +128,7 @@ unsafe extern "C" {
     pub fn lbm_read_distributions(sim: *mut LbmSim, which: i32, dst: *mut f32) -> c_int;
     pub fn lbm_write_distributions(sim: *mut LbmSim, which: i32, src: *const f32) -> c_int;
     pub fn lbm_read_macro(sim: *mut LbmSim, format: i32, dst: *mut c_void) -> c_int;
+    pub fn lbm_read_macro_async(sim: *mut LbmSim, dst: *mut c_void) -> c_int;
     pub fn lbm_read_lattice_info(sim: *mut LbmSim, dst: *mut LatticeInfo) -> c_int;
     pub fn lbm_total_mass(sim: *mut LbmSim, which: i32, out: *mut f64) -> c_int;
 

@@ -55,6 +55,13 @@ struct LbmSim {
     double *d_mass = nullptr;
     float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
     __half *scratch16 = nullptr; // RGBA16F texels for the on-demand macro read
+    // second macro texture + copy stream for lbm_read_macro_async (pipelined field read-back)
+    __half *macro_buf[2] = {nullptr, nullptr};
+    int macro_cur = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_copied[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    uint64_t macro_writes = 0, macro_writes_at_flip = ~0ull; // to serve the newest texture after a flip
     float *scratch_dense = nullptr; // 9 dense planes: canonical view of an AA state in its shifted layout
     bool aa = false;
     uint64_t steps_since_reset = 0;
@@ -198,6 +205,7 @@ int launch_step(LbmSim *s, int rb) {
         s->launches += n;
     }
     s->steps_since_reset++;
+    s->macro_writes++;
     return LBM_OK;
 }
 
@@ -237,7 +245,7 @@ int launch_particles(LbmSim *s) {
 // Captures `body` (kernel launches on s->stream) into an executable graph.
 template <typename F>
 int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
-    const uint64_t launches = s->launches, since = s->steps_since_reset;
+    const uint64_t launches = s->launches, since = s->steps_since_reset, writes = s->macro_writes;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = body();
     cudaGraph_t g = nullptr;
@@ -245,6 +253,7 @@ int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
     *kernels = s->launches - launches;
     s->launches = launches; // nothing ran yet
     s->steps_since_reset = since;
+    s->macro_writes = writes;
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, g, 0);
@@ -291,7 +300,12 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->P.cls);
     cudaFree(s->P.nbr);
     cudaFree(s->P.info);
-    cudaFree(s->P.macro16);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    cudaFree(s->macro_buf[0] ? s->macro_buf[0] : s->P.macro16);
+    cudaFree(s->macro_buf[1]);
+    if (s->ev_ready) cudaEventDestroy(s->ev_ready);
+    for (auto e : s->ev_copied) if (e) cudaEventDestroy(e);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     cudaFree(s->scratch32);
     cudaFree(s->scratch16);
     cudaFree(s->scratch_dense);
@@ -370,6 +384,7 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     if (d.flags & LBM_FLAG_MACRO_EVERY_STEP) {
         CU(cudaMalloc(&P.macro16, sizeof(__half) * 4 * (size_t)P.h * P.nx));
         CU(cudaMemsetAsync(P.macro16, 0, sizeof(__half) * 4 * (size_t)P.h * P.nx, s->stream));
+        s->macro_buf[0] = P.macro16;
     }
     CU(cudaMalloc(&s->d_mass, sizeof(double)));
     s->mixed.warps_per_row = (d.nx + 127) / 128;
@@ -507,6 +522,7 @@ extern "C" int lbm_reset(LbmSim *s) {
     if (rc) return rc;
     s->swap = 0;
     s->steps_since_reset = 0;
+    s->macro_writes++; // init.wgsl:62 rewrites the texture
     // init.wgsl:51-59 may have turned armed force cells back into bulk
     return derive_rows(s, 0, s->P.h);
 }
@@ -550,6 +566,7 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
             CU(cudaGraphLaunch(g, s->stream));
             s->launches += s->graph_steps_kernels[s->swap];
             s->steps_since_reset += kGraphSteps;
+            s->macro_writes += kGraphSteps;
         }
     }
     for (int i = 0; i < left; i++) {
@@ -594,6 +611,7 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
             CU(cudaGraphLaunch(s->graph_frame, s->stream));
             s->launches += s->graph_frame_kernels;
             s->steps_since_reset += 2;
+            s->macro_writes += 2;
         } else {
             rc = frame();
             if (rc) return rc;
@@ -611,6 +629,10 @@ extern "C" int lbm_sync(LbmSim *s) {
     if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    if (s->copy_stream) {
+        CU(cudaStreamSynchronize(s->copy_stream));
+        s->copy_pending[0] = s->copy_pending[1] = false;
+    }
     if (s->d.world > 1) {
         // sticky word set by an edge CTA whose wait for a neighbour slab ran into the 4 s bound
         unsigned int timed_out = 0;
@@ -673,8 +695,10 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
     if (format == LBM_MACRO_RGBA16F && P.macro16) {
-        // written by the step itself (LBM_FLAG_MACRO_EVERY_STEP)
-        CU(cudaMemcpyAsync(dst, P.macro16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+        // written by the step itself (LBM_FLAG_MACRO_EVERY_STEP); right after lbm_read_macro_async switched
+        // textures the newest field is still in the other one
+        const __half *newest = (s->macro_writes == s->macro_writes_at_flip) ? s->macro_buf[s->macro_cur ^ 1] : P.macro16;
+        CU(cudaMemcpyAsync(dst, newest, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         return LBM_OK;
     }
@@ -710,6 +734,34 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
     else
         CU(cudaMemcpyAsync(dst, Q.macro16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// Pipelined read-back of the RGBA16F macro texture: the copy runs on its own stream while the handle
+// goes on stepping into a second texture.  dst must stay valid (and should be pinned) until lbm_sync.
+extern "C" int lbm_read_macro_async(LbmSim *s, void *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (!s->P.macro16) return fail(s, LBM_ERR_STATE, "lbm_read_macro_async needs LBM_FLAG_MACRO_EVERY_STEP");
+    CU(cudaSetDevice(s->device));
+    const size_t bytes = sizeof(__half) * 4 * (size_t)s->P.h * s->P.nx;
+    if (!s->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming));
+        for (auto &e : s->ev_copied) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaMalloc(&s->macro_buf[1], bytes));
+    }
+    const int cur = s->macro_cur, nxt = cur ^ 1;
+    CU(cudaEventRecord(s->ev_ready, s->stream));              // texture `cur` is final once the queued steps ran
+    CU(cudaStreamWaitEvent(s->copy_stream, s->ev_ready, 0));
+    CU(cudaMemcpyAsync(dst, s->macro_buf[cur], bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(s->ev_copied[cur], s->copy_stream));
+    s->copy_pending[cur] = true;
+    // later steps write the other texture, once the copy that may still read it has finished
+    if (s->copy_pending[nxt]) CU(cudaStreamWaitEvent(s->stream, s->ev_copied[nxt], 0));
+    s->macro_cur = nxt;
+    s->P.macro16 = s->macro_buf[nxt];
+    s->macro_writes_at_flip = s->macro_writes;
+    invalidate_graphs(s); // the texture pointer is baked into captured launches
     return LBM_OK;
 }
 

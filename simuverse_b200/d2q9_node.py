@@ -240,6 +240,11 @@ class D2Q9Node:
         check(lib.lbm_read_macro(self._h, _capi.MACRO_RGBA16F, ptr(out)), self._h)
         return out
 
+    def read_macro_tex_async(self, out):
+        """Enqueue the texture read-back into ``out`` ((rows, nx, 4) float16, ideally pinned); complete after sync()."""
+        assert out.dtype == np.float16 and out.size == self.rows * self.lattice[0] * 4 and out.flags["C_CONTIGUOUS"]
+        check(lib.lbm_read_macro_async(self._h, ptr(out)), self._h)
+
     def read_lattice_info(self):
         out = np.empty(self.rows * self.lattice[0], dtype=LATTICE_INFO_DTYPE)
         check(lib.lbm_read_lattice_info(self._h, ptr(out)), self._h)

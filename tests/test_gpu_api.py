@@ -277,3 +277,31 @@ def test_lost_neighbour_times_out_instead_of_hanging(orc):
     b.sync()
     a.close()
     b.close()
+
+
+def test_pipelined_macro_readback(orc):
+    """lbm_read_macro_async: the field of frame k is copied out while frame k+1 is computed into a second
+    texture; every delivered field equals the oracle's texture of that frame."""
+    nx, ny = 256, 160
+    info = orc.init_lattice_material(nx, ny, W.POISEUILLE)
+    node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.POISEUILLE), lattice=(nx, ny), lattice_info=info,
+                       flags=sb.FLAG_MACRO_EVERY_STEP)
+    sim = oracle_for(orc, nx, ny, info)
+    outs = [np.zeros((ny, nx, 4), np.float16) for _ in range(5)]
+    want = []
+    for k in range(5):
+        node.compute_frames(1)
+        node.read_macro_tex_async(outs[k])
+        sim.step(2)
+        want.append(sim.macro_f16.copy())
+    # right after the texture switch the synchronous read must still return the newest field
+    np.testing.assert_array_equal(node.read_macro_tex().view(np.uint16).reshape(-1), want[-1])
+    node.sync()
+    for k in range(5):
+        np.testing.assert_array_equal(outs[k].view(np.uint16).reshape(-1), want[k])
+    node.step_n(40)  # graphs are rebuilt on the new texture
+    sim.step(40)
+    np.testing.assert_array_equal(node.read_macro_tex().view(np.uint16).reshape(-1), sim.macro_f16)
+    for which in (0, 1):
+        assert_bits_equal(node.read_distributions(which), sim.distributions(which), "state")
+    node.close()
