@@ -83,7 +83,16 @@ def case_particles():
     return dict(nx=nx, ny=ny, fluid_ty=0, info=channel(nx, ny), steps=40, post=[], particles=(9, 6))
 
 
-CASES = {"wgsl_channel_72x48_s40": case_channel, "wgsl_cavity_40x32_s40": case_cavity,
+def case_midrun():
+    """add_obstacle-style mask change in the middle of a run: the new solid cells keep their last
+    distributions, which their neighbours pull for exactly one more step."""
+    nx, ny = 48, 36
+    c = dict(nx=nx, ny=ny, fluid_ty=0, info=channel(nx, ny), steps=44, post=[])
+    c["midrun"] = dict(after=21, x0=30, x1=36, y0=14, y1=21)
+    return c
+
+
+CASES = {"wgsl_midrun_48x36_s44": case_midrun, "wgsl_channel_72x48_s40": case_channel, "wgsl_cavity_40x32_s40": case_cavity,
          "wgsl_force_36x30_s100": case_force, "wgsl_periodic_22x14_s30": case_periodic,
          "wgsl_particles_60x40_f20": case_particles}
 
@@ -91,7 +100,10 @@ CASES = {"wgsl_channel_72x48_s40": case_channel, "wgsl_cavity_40x32_s40": case_c
 def main():
     if not H.available():
         raise SystemExit("needs the reference tree at /root/reference")
+    only = sys.argv[1:]
     for name, make in CASES.items():
+        if only and name not in only:
+            continue
         t0 = time.time()
         c = make()
         nx, ny = c["nx"], c["ny"]
@@ -117,6 +129,13 @@ def main():
                 sim.step(1)
                 sim.particle_update()
             extra.update(particles=parts, canvas=canvas, particle_num=np.array(num))
+        elif "midrun" in c:
+            m = c["midrun"]
+            sim.step(m["after"])
+            g2 = sim.info.reshape(ny, nx)
+            g2[m["y0"]:m["y1"], m["x0"]:m["x1"]] = (W.OBSTACLE, -1, 0.0, 0.0)  # queue.write_buffer(info_buf, ..)
+            sim.step(c["steps"] - m["after"])
+            extra.update(midrun=np.array([m["after"], m["x0"], m["x1"], m["y0"], m["y1"]]))
         else:
             sim.step(c["steps"])
         out = os.path.join(HERE, name + ".npz")
