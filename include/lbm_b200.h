@@ -76,6 +76,12 @@ typedef enum LbmStatus {
 #define LBM_FLAG_NO_GRAPH         0x4u /* launch every kernel individually instead of replaying CUDA
                                           graphs of 16 steps / one frame (A/B testing) */
 
+#define LBM_FLAG_NO_FUSE          0x10u /* never run two updates as one sweep (lbm_fused.cuh); by default lbm_step_n and
+                                          lbm_compute_frames do so whenever nothing has to happen between the two
+                                          updates (no tracer particles / per-update macro texture, no force cell
+                                          counting down).  Results are identical either way; the buffer that is not
+                                          current is recomputed on demand when it is read (A/B testing) */
+
 /* lbm_read_macro formats */
 #define LBM_MACRO_F32_PLANES 0 /* 3 planes (u.x, u.y, rho) of rows*nx f32, before the f16 store */
 #define LBM_MACRO_RGBA16F    1 /* rows*nx texels of 4 halfs (u.x, u.y, rho, 1), the reference texture */
@@ -166,6 +172,8 @@ int lbm_ipc_attach(LbmSim *sim, const LbmIpcBlob *up, const LbmIpcBlob *down);
 /* ------------------------------------------------------------------ timing / introspection */
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 uint64_t lbm_launch_count(const LbmSim *sim);
+/* How many of those launches were two-update sweeps (k_frame2), i.e. advanced the lattice by two updates. */
+uint64_t lbm_fused_sweep_count(const LbmSim *sim);
 /* Device time of the last lbm_step_n call in milliseconds, measured with CUDA events on the
  * handle's own stream (torch.cuda.Event only sees torch's current stream). */
 int lbm_last_step_n_ms(LbmSim *sim, float *ms);

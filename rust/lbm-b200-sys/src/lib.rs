@@ -101,6 +101,7 @@ pub const LBM_FLAG_MACRO_EVERY_STEP: u32 = 0x1;
 pub const LBM_FLAG_KERNEL_GENERIC: u32 = 0x2;
 pub const LBM_FLAG_NO_GRAPH: u32 = 0x4;
 pub const LBM_FLAG_AA: u32 = 0x8;
+pub const LBM_FLAG_NO_FUSE: u32 = 0x10;
 pub const LBM_MACRO_F32_PLANES: i32 = 0;
 pub const LBM_MACRO_RGBA16F: i32 = 1;
 
@@ -144,6 +145,7 @@ unsafe extern "C" {
     pub fn lbm_ipc_attach(sim: *mut LbmSim, up: *const LbmIpcBlob, down: *const LbmIpcBlob) -> c_int;
 
     pub fn lbm_launch_count(sim: *const LbmSim) -> u64;
+    pub fn lbm_fused_sweep_count(sim: *const LbmSim) -> u64;
     pub fn lbm_last_step_n_ms(sim: *mut LbmSim, ms: *mut f32) -> c_int;
     pub fn lbm_stream(sim: *mut LbmSim) -> *mut c_void;
 }

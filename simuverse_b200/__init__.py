@@ -7,7 +7,7 @@ interface over that ABI.  Importing it loads ``_native/liblbm_b200.so`` and fail
 library has not been built: there is no CPU / PyTorch fallback.
 """
 from . import wire
-from ._capi import (FLAG_KERNEL_GENERIC, FLAG_MACRO_EVERY_STEP, FLAG_NO_GRAPH, FLAG_AA, LIB_PATH, MACRO_F32_PLANES, MACRO_RGBA16F,
+from ._capi import (FLAG_KERNEL_GENERIC, FLAG_MACRO_EVERY_STEP, FLAG_NO_GRAPH, FLAG_AA, FLAG_NO_FUSE, LIB_PATH, MACRO_F32_PLANES, MACRO_RGBA16F,
                     PRESET_POROUS, LbmError, lib)
 from .d2q9_node import D2Q9Node, SettingObj, init_lattice_material, init_porous_material, lbm_uniform_new
 from .fluid_simulator import FluidSimulator, init_trajectory_particles, particle_grid
@@ -15,5 +15,5 @@ from .fluid_simulator import FluidSimulator, init_trajectory_particles, particle
 __all__ = [
     "D2Q9Node", "FluidSimulator", "SettingObj", "LbmError", "init_lattice_material", "init_porous_material",
     "lbm_uniform_new", "init_trajectory_particles", "particle_grid", "wire", "lib", "LIB_PATH",
-    "FLAG_KERNEL_GENERIC", "FLAG_MACRO_EVERY_STEP", "FLAG_NO_GRAPH", "FLAG_AA", "MACRO_F32_PLANES", "MACRO_RGBA16F", "PRESET_POROUS",
+    "FLAG_KERNEL_GENERIC", "FLAG_MACRO_EVERY_STEP", "FLAG_NO_GRAPH", "FLAG_AA", "FLAG_NO_FUSE", "MACRO_F32_PLANES", "MACRO_RGBA16F", "PRESET_POROUS",
 ]

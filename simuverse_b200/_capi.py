@@ -19,6 +19,7 @@ FLAG_MACRO_EVERY_STEP = 0x1
 FLAG_KERNEL_GENERIC = 0x2
 FLAG_NO_GRAPH = 0x4
 FLAG_AA = 0x8
+FLAG_NO_FUSE = 0x10
 MACRO_F32_PLANES, MACRO_RGBA16F = 0, 1
 PRESET_POROUS = 100
 
@@ -86,6 +87,7 @@ PROTOTYPES = {
     "lbm_ipc_export": (C.c_int, [_H, C.POINTER(LbmIpcBlob)]),
     "lbm_ipc_attach": (C.c_int, [_H, C.POINTER(LbmIpcBlob), C.POINTER(LbmIpcBlob)]),
     "lbm_launch_count": (_u64, [_H]),
+    "lbm_fused_sweep_count": (_u64, [_H]),
     "lbm_last_step_n_ms": (C.c_int, [_H, C.POINTER(_f32)]),
     "lbm_stream": (_vp, [_H]),
     # host-side mirrors

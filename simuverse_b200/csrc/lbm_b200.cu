@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -15,6 +16,7 @@
 #include "lbm_particles.cuh"
 #include "lbm_step_vec.cuh"
 #include "lbm_aa.cuh"
+#include "lbm_fused.cuh"
 
 using namespace lbm;
 
@@ -89,6 +91,20 @@ struct LbmSim {
     cudaGraphExec_t graph_frame = nullptr;
     uint64_t graph_steps_kernels[2] = {0, 0}; // kernels inside each captured graph (gpu_launches accounting)
     uint64_t graph_frame_kernels = 0;
+    // two updates per sweep (lbm_fused.cuh)
+    FuseGeom fuse{};
+    int *d_fuse_rows = nullptr;            // FuseGeom::row_start
+    unsigned int *d_fuse_flags = nullptr;  // [0] largest armed block_iter seen by k_derive, [1] k_ring_check verdict
+    uint8_t *cls_halo = nullptr;           // multi-slab: class rows y0-1 and y0+h (2 * pitch bytes)
+    int64_t countdown_left = 0;            // upper bound of the updates during which a force cell may still count down / retire
+    bool fuse_blocked = false;             // a ring cell would pull a stale value out of a solid (see k_ring_check)
+    bool ring_check_needed = false;
+    bool mask_written_since_reset = false;
+    bool prev_stale = false;               // after a two-update sweep the non-current buffer holds t, not t+1
+    int flip = 0;                          // parity of the buffer-pointer exchanges done by two-update sweeps
+    cudaGraphExec_t graph_pairs[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + swap]: kGraphSteps / 2 sweeps
+    uint64_t graph_pairs_kernels[4] = {0, 0, 0, 0};
+    uint64_t fused_sweeps = 0;
     std::string err;
 };
 
@@ -130,9 +146,22 @@ int derive_rows(LbmSim *s, int l0, int l1) {
     l1 = std::min(l1, s->P.h);
     if (l0 >= l1) return LBM_OK;
     dim3 block(64, 4);
-    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1);
+    CU(cudaMemsetAsync(s->d_fuse_flags, 0, sizeof(unsigned int), s->stream));
+    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, s->d_fuse_flags);
     int rc = check_launch(s, "k_derive");
     if (rc) return rc;
+    if (s->cls_halo) {
+        k_derive_halo<<<(s->P.pitch + 255) / 256, 256, 0, s->stream>>>(s->P, s->cls_halo, s->cls_halo + s->P.pitch);
+        if ((rc = check_launch(s, "k_derive_halo"))) return rc;
+    }
+    {
+        unsigned int armed = 0;
+        CU(cudaMemcpyAsync(&armed, s->d_fuse_flags, sizeof(armed), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        // a cell armed with k counts down during k updates and is retired (CLS_FLIPPED) by the one after
+        if (armed) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
+    }
+    if (s->mask_written_since_reset) s->ring_check_needed = true;
     // the mask changed: rebuild the list of warps k_step_vec leaves to k_step_mixed
     MixedList &M = s->mixed;
     if (M.total > 0) {
@@ -206,6 +235,8 @@ int launch_step(LbmSim *s, int rb) {
     }
     s->steps_since_reset++;
     s->macro_writes++;
+    s->prev_stale = false; // the buffer just written is the true t+1 again
+    if (s->countdown_left > 0) s->countdown_left--;
     return LBM_OK;
 }
 
@@ -230,6 +261,8 @@ void invalidate_graphs(LbmSim *s) {
     for (auto &g : s->graph_steps)
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     if (s->graph_frame) { cudaGraphExecDestroy(s->graph_frame); s->graph_frame = nullptr; }
+    for (auto &g : s->graph_pairs)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
 // (multi-slab launches are replayable too: the step counter the edge CTAs compare against lives on the device)
@@ -242,10 +275,153 @@ int launch_particles(LbmSim *s) {
     return LBM_OK;
 }
 
+
+// ------------------------------------------------------------------ two updates per sweep (lbm_fused.cuh)
+
+// After a sweep the new state sits in the buffer the sweep wrote; two reference updates would have left it in
+// the buffer they started from.  Exchanging the pointers restores that labelling (the swap index is unchanged).
+void exchange_buffers(LbmSim *s) {
+    std::swap(s->P.f[0], s->P.f[1]);
+    std::swap(s->P.up[0], s->P.up[1]);
+    std::swap(s->P.dn[0], s->P.dn[1]);
+    std::swap(s->f_off[0], s->f_off[1]);
+    s->flip ^= 1;
+}
+
+// Work items of a sweep: every strip (a warp, 60 output columns) is cut into row blocks, and each block costs two
+// redundant rows of update 1.
+int fuse_geometry(LbmSim *s) {
+    FuseGeom &g = s->fuse;
+    const int G = s->P.nx / kFuseCells;
+    const int h = s->P.h;
+    g.strips = (G + kFuseOut - 1) / kFuseOut;
+    g.ctas_x = (g.strips + kFuseWarps - 1) / kFuseWarps;
+    std::vector<int> starts, starts0;
+    int fixed = 0, fixed0 = 8;
+    if (const char *e = getenv("LBM_FUSE_ROWS")) fixed = atoi(e);   // uniform height (tests, tuning)
+    if (const char *e = getenv("LBM_FUSE_ROWS0")) fixed0 = std::max(1, atoi(e));
+    if (fixed > 0) {
+        for (int y = 0; y < h; y += fixed) starts.push_back(y);
+        fixed0 = std::min(fixed0, fixed);
+    } else {
+        int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true>, kFuseThreads, 0);
+        // Uniform height giving at least ~6 waves of CTAs (measured on B200: with fewer the sweep ends in a long
+        // tail; 4096^2 is best at 16 rows, 16384^2 at 32), between 8 and 32 rows.
+        int h_min = 8, h_max = 32;
+        if (const char *e = getenv("LBM_FUSE_HMIN")) h_min = std::max(1, atoi(e));
+        if (const char *e = getenv("LBM_FUSE_HMAX")) h_max = std::max(h_min, atoi(e));
+        const long long resident = (long long)sms * std::max(per_sm, 1);
+        int H = (int)((long long)h * g.ctas_x / (6 * resident));
+        H = std::max(h_min, std::min(H, h_max));
+        for (int y = 0; y < h; y += H) starts.push_back(y);
+    }
+    g.rowblocks = (int)starts.size();
+    starts.push_back(h);
+    // the first strip column (the inlet column of a channel) in short blocks: see k_frame2
+    for (int y = 0; y < h; y += fixed0) starts0.push_back(y);
+    g.rowblocks0 = (int)starts0.size();
+    starts0.push_back(h);
+    if (g.ctas_x == 1) { // a single strip column: everything is "column 0"
+        starts0 = starts;
+        g.rowblocks0 = g.rowblocks;
+        g.rowblocks = 0;
+    }
+    starts0.insert(starts0.end(), starts.begin(), starts.end());
+    starts.swap(starts0);
+    if (s->d_fuse_rows) { cudaFree(s->d_fuse_rows); s->d_fuse_rows = nullptr; }
+    CU(cudaMalloc(&s->d_fuse_rows, sizeof(int) * starts.size()));
+    CU(cudaMemcpy(s->d_fuse_rows, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice));
+    g.row_start = s->d_fuse_rows;
+    return LBM_OK;
+}
+
+int run_ring_check(LbmSim *s) {
+    CU(cudaMemsetAsync(s->d_fuse_flags + 1, 0, sizeof(unsigned int), s->stream));
+    k_ring_check<<<64, 256, 0, s->stream>>>(s->P, s->d_fuse_flags + 1);
+    int rc = check_launch(s, "k_ring_check");
+    if (rc) return rc;
+    unsigned int stale = 0;
+    CU(cudaMemcpyAsync(&stale, s->d_fuse_flags + 1, sizeof(stale), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    s->fuse_blocked = stale != 0;
+    s->ring_check_needed = false;
+    return LBM_OK;
+}
+
+// May the next two updates run as one sweep?  (see the header comment of lbm_fused.cuh)
+bool fuse_possible(const LbmSim *s) {
+    return !s->aa && !(s->d.flags & (LBM_FLAG_KERNEL_GENERIC | LBM_FLAG_NO_FUSE | LBM_FLAG_MACRO_EVERY_STEP)) &&
+           s->d.world == 1 && (s->P.nx % kFuseCells) == 0 && s->P.h >= 4 && !s->P.macro16 && !s->P.macro32;
+}
+
+int fuse_eligible(LbmSim *s, bool *ok) {
+    *ok = false;
+    if (!fuse_possible(s) || s->countdown_left > 0) return LBM_OK;
+    if (s->ring_check_needed) {
+        int rc = run_ring_check(s);
+        if (rc) return rc;
+    }
+    *ok = !s->fuse_blocked;
+    return LBM_OK;
+}
+
+// Two updates starting from buffer `first`: ONE launch, then the pointer exchange.
+int launch_pair(LbmSim *s, int first) {
+    const FuseGeom &g = s->fuse;
+    const long long blocks = (long long)g.rowblocks0 + (long long)g.rowblocks * (g.ctas_x - 1);
+    if (blocks > 2147483647ll) return fail(s, LBM_ERR_INVALID_ARG, "lattice too large for one sweep launch");
+    // rho * w is shared between the directions of equal weight when the uploaded weights allow it
+    const Coef &k = s->P.k;
+    const bool symw = k.w[1] == k.w[2] && k.w[1] == k.w[3] && k.w[1] == k.w[4] && k.w[5] == k.w[6] && k.w[5] == k.w[7] &&
+                      k.w[5] == k.w[8];
+    if (symw) k_frame2<true><<<(unsigned int)blocks, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    else k_frame2<false><<<(unsigned int)blocks, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    int rc = check_launch(s, "k_frame2");
+    if (rc) return rc;
+    exchange_buffers(s);
+    s->steps_since_reset += 2;
+    s->macro_writes += 2;
+    s->fused_sweeps++;
+    s->prev_stale = true;
+    return LBM_OK;
+}
+
+// The non-current buffer after a sweep holds the state two updates back.  Whoever needs what the reference has
+// there (the state one update back: lbm_read_distributions(previous), the on-demand macro field, ...) gets it
+// recomputed: one ordinary update from t into a temporary, copied over the stale buffer.
+int materialize_prev(LbmSim *s) {
+    if (!s->prev_stale) return LBM_OK;
+    const SlabParams &P = s->P;
+    const int cur = s->swap, old = s->swap ^ 1;
+    float *tmp = nullptr;
+    const size_t bytes = sizeof(float) * 9 * P.plane;
+    CU(cudaMalloc(&tmp, bytes));
+    cudaError_t e = cudaMemsetAsync(tmp, 0, bytes, s->stream);
+    SlabParams Q = P;
+    Q.f[0] = P.f[old]; Q.up[0] = P.up[old]; Q.dn[0] = P.dn[old];
+    Q.f[1] = tmp; Q.up[1] = tmp + (size_t)(P.h - 1) * P.pitch; Q.dn[1] = tmp;
+    Q.macro16 = nullptr; Q.macro32 = nullptr;
+    int n = 0;
+    if (e == cudaSuccess) e = launch_step_vec(Q, s->sync, s->mixed, 0, s->stream, &n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(P.f[old], tmp, bytes, cudaMemcpyDeviceToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "recomputing the previous buffer failed: %s", cudaGetErrorString(e));
+    s->launches += n;
+    s->prev_stale = false;
+    (void)cur;
+    return LBM_OK;
+}
+
 // Captures `body` (kernel launches on s->stream) into an executable graph.
 template <typename F>
 int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
-    const uint64_t launches = s->launches, since = s->steps_since_reset, writes = s->macro_writes;
+    const uint64_t launches = s->launches, since = s->steps_since_reset, writes = s->macro_writes, sweeps = s->fused_sweeps;
+    const int64_t countdown = s->countdown_left;
+    const bool stale = s->prev_stale;
+    const int flip = s->flip;
     CU(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = body();
     cudaGraph_t g = nullptr;
@@ -254,6 +430,10 @@ int capture_graph(LbmSim *s, cudaGraphExec_t *out, uint64_t *kernels, F body) {
     s->launches = launches; // nothing ran yet
     s->steps_since_reset = since;
     s->macro_writes = writes;
+    s->fused_sweeps = sweeps;
+    s->countdown_left = countdown;
+    s->prev_stale = stale;
+    if (s->flip != flip) exchange_buffers(s); // a captured body must contain an even number of sweeps; be safe anyway
     if (rc) { if (g) cudaGraphDestroy(g); return rc; }
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, g, 0);
@@ -310,6 +490,9 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->scratch16);
     cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
+    cudaFree(s->d_fuse_flags);
+    cudaFree(s->d_fuse_rows);
+    cudaFree(s->cls_halo);
     cudaFree(s->mixed.list);
     cudaFree(s->mixed.count_dev);
     cudaFree(s->particles);
@@ -378,6 +561,17 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     CU(cudaMalloc(&P.nbr, cells));
     CU(cudaMemsetAsync(P.cls, CLS_SOLID, cells, s->stream));
     CU(cudaMemsetAsync(P.nbr, 0, cells, s->stream));
+    CU(cudaMalloc(&s->d_fuse_flags, 2 * sizeof(unsigned int)));
+    CU(cudaMemsetAsync(s->d_fuse_flags, 0, 2 * sizeof(unsigned int), s->stream));
+    if (d.world > 1) {
+        CU(cudaMalloc(&s->cls_halo, 2 * (size_t)P.pitch));
+        CU(cudaMemsetAsync(s->cls_halo, CLS_SOLID, 2 * (size_t)P.pitch, s->stream));
+        P.cls_up = s->cls_halo;
+        P.cls_dn = s->cls_halo + P.pitch;
+    } else { // periodic wrap: the halo rows are the own rows h-1 and 0
+        P.cls_up = P.cls + (size_t)(P.h - 1) * P.pitch;
+        P.cls_dn = P.cls;
+    }
     const size_t info_bytes = sizeof(LatticeInfo) * (size_t)(P.h + 2) * P.nx;
     CU(cudaMalloc(&P.info, info_bytes));
     CU(cudaMemsetAsync(P.info, 0, info_bytes, s->stream));
@@ -408,6 +602,10 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
 
     s->sync.flags = reinterpret_cast<unsigned int *>(s->arena + s->flag_off);
     s->sync.world = d.world;
+    {
+        int rc = fuse_geometry(s);
+        if (rc) return rc;
+    }
     CU(cudaStreamSynchronize(s->stream));
     return LBM_OK;
 }
@@ -466,6 +664,11 @@ extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const voi
                     (unsigned long long)nbytes, (unsigned long long)byte_offset, (unsigned long long)total);
     if (nbytes == 0) return LBM_OK;
     CU(cudaSetDevice(s->device));
+    {   // a solid painted over live fluid keeps that cell's values in BOTH buffers (ring cells may pull them for
+        // ever): the buffer that is not current must hold what the reference holds there, not the state of t-2
+        int rc = materialize_prev(s);
+        if (rc) return rc;
+    }
     const uint64_t lo = byte_offset, hi = byte_offset + nbytes;
     int touched_lo = P.h + 2, touched_hi = -1; // halo-indexed rows r = 0..h+1
     // (halo-indexed local row range, global first row) of the three pieces this slab keeps
@@ -523,8 +726,16 @@ extern "C" int lbm_reset(LbmSim *s) {
     s->swap = 0;
     s->steps_since_reset = 0;
     s->macro_writes++; // init.wgsl:62 rewrites the texture
+    // both buffers are freshly written: solids hold zeros, nothing is armed
+    s->prev_stale = false;
+    s->countdown_left = 0;
+    s->fuse_blocked = false;
+    s->ring_check_needed = false;
+    s->mask_written_since_reset = false;
     // init.wgsl:51-59 may have turned armed force cells back into bulk
-    return derive_rows(s, 0, s->P.h);
+    rc = derive_rows(s, 0, s->P.h);
+    s->mask_written_since_reset = true; // every later mask write may paint a solid over live fluid
+    return rc;
 }
 
 extern "C" int lbm_step(LbmSim *s, int32_t swap_index) {
@@ -535,10 +746,34 @@ extern "C" int lbm_step(LbmSim *s, int32_t swap_index) {
     if (s->aa && swap_index != s->swap)
         return fail(s, LBM_ERR_STATE, "in-place (AA) state is in layout %d: the next step must use swap_index %d", s->swap, s->swap);
     CU(cudaSetDevice(s->device));
+    if (swap_index != s->swap && (rc = materialize_prev(s))) return rc; // stepping from the previous buffer
     rc = launch_step(s, swap_index);
     if (rc) return rc;
     s->swap = swap_index ^ 1;
     return LBM_OK;
+}
+
+// Builds (once) the graph of kGraphSteps / 2 two-update sweeps for the current pointer / swap state.
+static int ensure_pair_graph(LbmSim *s) {
+    const int key = s->flip * 2 + s->swap;
+    if (s->graph_pairs[key]) return LBM_OK;
+    const int first = s->swap;
+    return capture_graph(s, &s->graph_pairs[key], &s->graph_pairs_kernels[key], [&]() {
+        int r = LBM_OK;
+        for (int i = 0; i < kGraphSteps / 2 && r == LBM_OK; i++) r = launch_pair(s, first);
+        return r;
+    });
+}
+
+static int ensure_step_graph(LbmSim *s) {
+    cudaGraphExec_t &g = s->graph_steps[s->swap];
+    if (g) return LBM_OK;
+    const int first = s->swap;
+    return capture_graph(s, &g, &s->graph_steps_kernels[s->swap], [&]() {
+        int r = LBM_OK;
+        for (int i = 0; i < kGraphSteps && r == LBM_OK; i++) r = launch_step(s, first ^ (i & 1));
+        return r;
+    });
 }
 
 extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
@@ -547,31 +782,53 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
     if (rc) return rc;
     CU(cudaSetDevice(s->device));
     int left = n;
-    if (graphs_enabled(s) && n >= 2 * kGraphSteps) {
-        cudaGraphExec_t &g = s->graph_steps[s->swap];
-        if (!g) {
-            const int first = s->swap;
-            rc = capture_graph(s, &g, &s->graph_steps_kernels[s->swap], [&]() {
-                int r = LBM_OK;
-                for (int i = 0; i < kGraphSteps && r == LBM_OK; i++) r = launch_step(s, first ^ (i & 1));
-                return r;
-            });
-            if (rc) return rc;
-        }
+    const bool graphs = graphs_enabled(s) && n >= 2 * kGraphSteps;
+    // decide and capture before the timed region starts (the common case: nothing is counting down)
+    bool fused = false;
+    if (left >= 2 && s->countdown_left == 0) {
+        if ((rc = fuse_eligible(s, &fused))) return rc;
+        if (graphs && (rc = fused ? ensure_pair_graph(s) : ensure_step_graph(s))) return rc;
     }
     CU(cudaEventRecord(s->ev0, s->stream));
-    if (graphs_enabled(s) && n >= 2 * kGraphSteps) {
+    if (s->countdown_left > 0 && fuse_possible(s)) {
+        // force cells that are still counting down mutate the info buffer between updates: single updates
+        while (left > 0 && s->countdown_left > 0) {
+            if ((rc = launch_step(s, s->swap))) return rc;
+            s->swap ^= 1;
+            left--;
+        }
+        if (left >= 2 && (rc = fuse_eligible(s, &fused))) return rc;
+    }
+    if (fused) {
+        // two updates per launch; the swap index is the same after every sweep
+        if (graphs && left >= 2 * kGraphSteps) {
+            if ((rc = ensure_pair_graph(s))) return rc;
+            const int key = s->flip * 2 + s->swap;
+            for (; left >= kGraphSteps; left -= kGraphSteps) { // an even number of sweeps: pointers unchanged
+                CU(cudaGraphLaunch(s->graph_pairs[key], s->stream));
+                s->launches += s->graph_pairs_kernels[key];
+                s->steps_since_reset += kGraphSteps;
+                s->macro_writes += kGraphSteps;
+                s->fused_sweeps += kGraphSteps / 2;
+                s->prev_stale = true;
+            }
+        }
+        for (; left >= 2; left -= 2)
+            if ((rc = launch_pair(s, s->swap))) return rc;
+    } else if (graphs && left >= 2 * kGraphSteps) {
+        if ((rc = ensure_step_graph(s))) return rc;
         cudaGraphExec_t g = s->graph_steps[s->swap];
         for (; left >= kGraphSteps; left -= kGraphSteps) { // an even number of steps: swap index unchanged
             CU(cudaGraphLaunch(g, s->stream));
             s->launches += s->graph_steps_kernels[s->swap];
             s->steps_since_reset += kGraphSteps;
             s->macro_writes += kGraphSteps;
+            s->prev_stale = false;
+            s->countdown_left = std::max<int64_t>(0, s->countdown_left - kGraphSteps);
         }
     }
-    for (int i = 0; i < left; i++) {
-        rc = launch_step(s, s->swap);
-        if (rc) return rc;
+    for (; left > 0; left--) {
+        if ((rc = launch_step(s, s->swap))) return rc;
         s->swap ^= 1;
     }
     CU(cudaEventRecord(s->ev1, s->stream));
@@ -600,6 +857,31 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
         if (r == LBM_OK && with_particles) r = launch_particles(s);
         return r;
     };
+    // without a per-update consumer (tracer particles, macro texture) a frame is one two-update sweep
+    bool fused = false;
+    if (!with_particles && n_frames > 0 && (rc = fuse_eligible(s, &fused))) return rc;
+    if (fused) {
+        int left = n_frames;
+        const bool graphs = graphs_enabled(s) && n_frames >= kGraphSteps;
+        if (graphs && (rc = ensure_pair_graph(s))) return rc;
+        CU(cudaEventRecord(s->ev0, s->stream));
+        if (graphs) {
+            const int key = s->flip * 2 + s->swap;
+            for (; left >= kGraphSteps / 2; left -= kGraphSteps / 2) {
+                CU(cudaGraphLaunch(s->graph_pairs[key], s->stream));
+                s->launches += s->graph_pairs_kernels[key];
+                s->steps_since_reset += kGraphSteps;
+                s->macro_writes += kGraphSteps;
+                s->fused_sweeps += kGraphSteps / 2;
+                s->prev_stale = true;
+            }
+        }
+        for (; left > 0; left--)
+            if ((rc = launch_pair(s, 0))) return rc;
+        CU(cudaEventRecord(s->ev1, s->stream));
+        s->timed = true;
+        return LBM_OK;
+    }
     const bool use_graph = graphs_enabled(s) && n_frames >= 4;
     if (use_graph && !s->graph_frame) {
         rc = capture_graph(s, &s->graph_frame, &s->graph_frame_kernels, frame);
@@ -612,6 +894,8 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
             s->launches += s->graph_frame_kernels;
             s->steps_since_reset += 2;
             s->macro_writes += 2;
+            s->prev_stale = false;
+            s->countdown_left = std::max<int64_t>(0, s->countdown_left - 2);
         } else {
             rc = frame();
             if (rc) return rc;
@@ -655,6 +939,10 @@ extern "C" int lbm_slab_rows(const LbmSim *s, int32_t *y0, int32_t *rows) {
 extern "C" int lbm_read_distributions(LbmSim *s, int32_t which, float *dst) {
     if (!s || !dst || (which != 0 && which != 1)) return fail(s, LBM_ERR_INVALID_ARG, "bad argument");
     CU(cudaSetDevice(s->device));
+    if (which != s->swap) { // the previous buffer: recompute it if the last launch was a two-update sweep
+        int rc = materialize_prev(s);
+        if (rc) return rc;
+    }
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
     if (s->aa) {
@@ -679,12 +967,17 @@ extern "C" int lbm_write_distributions(LbmSim *s, int32_t which, const float *sr
     if (s->aa && (which != 0 || s->swap != 0))
         return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: distributions can only be written as buffer 0 in the natural layout (after lbm_reset or an even number of steps)");
     CU(cudaSetDevice(s->device));
+    {   // keep the other buffer what the reference would hold there before this one is replaced
+        int rc = materialize_prev(s);
+        if (rc) return rc;
+    }
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
     for (int i = 0; i < 9; i++)
         CU(cudaMemcpy2DAsync(P.f[which] + i * P.plane, sizeof(float) * P.pitch, src + i * n, sizeof(float) * P.nx,
                              sizeof(float) * P.nx, P.h, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    s->ring_check_needed = true; // restored solids may hold values a ring cell pulls (k_ring_check)
     return LBM_OK;
 }
 
@@ -708,6 +1001,7 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
     // again yields exactly the (rho, u) that step computed (collide_stream.wgsl:43-74).
     int rc = ready_to_step(s);
     if (rc) return rc;
+    if ((rc = materialize_prev(s))) return rc; // after a two-update sweep that buffer is recomputed first
     SlabParams Q = P;
     if (format == LBM_MACRO_F32_PLANES) {
         rc = ensure_scratch32(s);
@@ -779,6 +1073,7 @@ extern "C" int lbm_total_mass(LbmSim *s, int32_t which, double *out) {
     CU(cudaSetDevice(s->device));
     CU(cudaMemsetAsync(s->d_mass, 0, sizeof(double), s->stream));
     int rc;
+    if (which != s->swap && (rc = materialize_prev(s))) return rc;
     if (s->aa && which != s->swap) return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: only the current state (which = %d) exists", s->swap);
     if (s->aa && s->swap == 1) {
         if ((rc = aa_canonical(s))) return rc;
@@ -938,6 +1233,7 @@ extern "C" int lbm_ipc_attach(LbmSim *s, const LbmIpcBlob *up, const LbmIpcBlob 
 // =================================================================== introspection
 
 extern "C" uint64_t lbm_launch_count(const LbmSim *s) { return s ? s->launches : 0; }
+extern "C" uint64_t lbm_fused_sweep_count(const LbmSim *s) { return s ? s->fused_sweeps : 0; }
 
 extern "C" int lbm_last_step_n_ms(LbmSim *s, float *ms) {
     if (!s || !ms) return fail(s, LBM_ERR_INVALID_ARG, "null argument");

@@ -61,6 +61,8 @@ struct SlabParams {
     size_t up_plane;   // plane stride of the memory `up` points into
     size_t dn_plane;
     uint8_t *cls;      // [l*pitch + x]
+    const uint8_t *cls_up; // class row of row y0-1 / y0+h (own wrapped rows when world==1, else a local copy
+    const uint8_t *cls_dn; // derived from the info halo rows); read by the two-update kernel only
     uint8_t *nbr;      // fluid cell: bit (i-1) set = strictly interior and cell+e_i is solid (bounce);
                        // solid cell: bit (k-1) set = slot k is dead (its only reader is solid too)
     LatticeInfo *info; // (h+2) rows of nx: row 0 = halo y0-1, rows 1..h owned, row h+1 = halo

@@ -51,12 +51,15 @@ __global__ void __launch_bounds__(256) k_init(const __grid_constant__ SlabParams
 
 // ------------------------------------------------------------------ class / neighbour planes
 // Derived from the authoritative LatticeInfo buffer for owned rows [l0, l1).
-__global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabParams P, int l0, int l1) {
+// armed (optional): receives the largest block_iter of the inlet / force cells seen (atomicMax) — the host
+// keeps the two-update kernel off while a countdown is running (collide_stream.wgsl:55-62).
+__global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabParams P, int l0, int l1, unsigned int *armed) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = l0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.nx || l >= l1) return;
     const LatticeInfo *row = P.info + (size_t)(l + 1) * P.nx;
     const int m = row[x].material;
+    if (armed && (m == 3 || m == 6) && row[x].block_iter > 0) atomicMax(armed, (unsigned int)row[x].block_iter);
     const int y = P.y0 + l;
     uint8_t nb = 0;
     const bool solid = (m == 2 || m == 4);
@@ -100,6 +103,54 @@ __global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabPara
     const size_t cl = (size_t)l * P.pitch + x;
     P.cls[cl] = c;
     P.nbr[cl] = nb;
+}
+
+// ------------------------------------------------------------------ class rows of the two halo rows
+// Rows y0-1 and y0+h as the two-update kernel sees them: only "solid / inlet-or-force / other" matters there
+// (update 1 of a neighbour row never consults the neighbour bits).  Derived from the info halo rows.
+__global__ void __launch_bounds__(256) k_derive_halo(const __grid_constant__ SlabParams P, uint8_t *up, uint8_t *dn) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= P.pitch) return;
+    uint8_t cu = CLS_SOLID, cd = CLS_SOLID; // pitch padding is never read
+    if (x < P.nx) {
+        const int mu = P.info[x].material, md = P.info[(size_t)(P.h + 1) * P.nx + x].material;
+        cu = (mu == 2 || mu == 4) ? CLS_SOLID : ((mu == 3 || mu == 6) ? CLS_ACCEL : CLS_FLUID_NB);
+        cd = (md == 2 || md == 4) ? CLS_SOLID : ((md == 3 || md == 6) ? CLS_ACCEL : CLS_FLUID_NB);
+    }
+    up[x] = cu;
+    dn[x] = cd;
+}
+
+// ------------------------------------------------------------------ stale values a ring cell would pull
+// A fluid cell on the outer ring never receives a bounce-back (boundary.wgsl:19), so when it pulls from a solid
+// neighbour it reads whatever that slot holds: 0 after init.wgsl, but a leftover value when the solid was painted
+// over live fluid (add_obstacle mid-run) or restored from a checkpoint.  The two-update kernel assumes 0; this
+// kernel raises *flag when either buffer holds anything else in such a slot, and the host then keeps to single updates.
+__global__ void __launch_bounds__(256) k_ring_check(const __grid_constant__ SlabParams P, unsigned int *flag) {
+    const long long per_row = 2;                       // x = 0 and x = nx-1 of every owned row
+    const long long n_cols = per_row * P.h;
+    const bool top = P.y0 == 0, bot = P.y0 + P.h == P.ny;
+    const long long n = n_cols + (top ? P.nx : 0) + (bot ? P.nx : 0);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        int x, l;
+        if (t < n_cols) { l = (int)(t >> 1); x = (t & 1) ? P.nx - 1 : 0; }
+        else if (top && t < n_cols + P.nx) { l = 0; x = (int)(t - n_cols); }
+        else { l = P.h - 1; x = (int)(t - n_cols - (top ? P.nx : 0)); }
+        const int mat = P.info[(size_t)(l + 1) * P.nx + x].material;
+        if (mat == 2 || mat == 4) continue;
+#pragma unroll
+        for (int j = 1; j < 9; j++) {
+            int xs = x - dir_ex(j);
+            if (xs < 0) xs = P.nx - 1; else if (xs >= P.nx) xs = 0;
+            const int ls = l - dir_ey(j);
+            const int ms = P.info[(size_t)(ls + 1) * P.nx + xs].material; // halo rows hold the wrapped / neighbour rows
+            if (ms != 2 && ms != 4) continue;
+            for (int b = 0; b < 2; b++) {
+                const RowRef rr = row_ref(P, b, ls);
+                if (rr.p[(size_t)j * rr.plane + xs] != 0.0f) atomicOr(flag, 1u);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ preset generators

@@ -266,6 +266,11 @@ class D2Q9Node:
     def launch_count(self):
         return int(lib.lbm_launch_count(self._h))
 
+    @property
+    def fused_sweep_count(self):
+        """Launches that advanced the lattice by two updates at once (csrc/lbm_fused.cuh)."""
+        return int(lib.lbm_fused_sweep_count(self._h))
+
     # ------------------------------------------------------------------ particles
     def write_particle_uniform(self, pu):
         check(lib.lbm_write_particle_uniform(self._h, C.byref(pu)), self._h)

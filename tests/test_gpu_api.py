@@ -44,7 +44,7 @@ def test_launch_regimes_match_oracle(orc, period, regime):
     nx, ny = 4096, 384  # 32 warps per row: ~3/32, ~9/32 and 32/32 of them mixed; > 8192 interior warps, so the
     # small-lattice rule (always inline) does not apply
     info = striped_mask(orc, nx, ny, period)
-    node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.CUSTOM), lattice=(nx, ny), lattice_info=info)
+    node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.CUSTOM), lattice=(nx, ny), lattice_info=info, flags=sb.FLAG_NO_FUSE)
     before = node.launch_count
     node.step_n(3)
     per_step = (node.launch_count - before) / 3
