@@ -133,6 +133,13 @@ int lbm_step_n(LbmSim *sim, int32_t n);             /* n steps alternating from 
  * step(1), particle update (the particle updates only if the handle has tracer particles). */
 int lbm_compute_frames(LbmSim *sim, int32_t n_frames);
 int lbm_swap_index(const LbmSim *sim);              /* buffer the next lbm_step_n step reads */
+/* After a two-update sweep the buffer that is not current holds the state two updates back; the calls that need what
+ * the reference has there (the state one update back: lbm_read_distributions / lbm_total_mass of that buffer,
+ * the on-demand lbm_read_macro, lbm_write_*, lbm_step from it) recompute it first by themselves.  On a multi-slab
+ * lattice that recomputation is an ordinary neighbour-synchronised update and therefore COLLECTIVE: call
+ * lbm_refresh_previous on every slab, then synchronise all slabs (lbm_sync + host barrier), then read.  A no-op when
+ * the last launch was not a sweep. */
+int lbm_refresh_previous(LbmSim *sim);
 int lbm_sync(LbmSim *sim);
 
 /* ------------------------------------------------------------------ read-back / restore */

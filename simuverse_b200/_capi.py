@@ -86,6 +86,7 @@ PROTOTYPES = {
     "lbm_canvas_read": (C.c_int, [_H, _vp]),
     "lbm_ipc_export": (C.c_int, [_H, C.POINTER(LbmIpcBlob)]),
     "lbm_ipc_attach": (C.c_int, [_H, C.POINTER(LbmIpcBlob), C.POINTER(LbmIpcBlob)]),
+    "lbm_refresh_previous": (C.c_int, [_H]),
     "lbm_launch_count": (_u64, [_H]),
     "lbm_fused_sweep_count": (_u64, [_H]),
     "lbm_last_step_n_ms": (C.c_int, [_H, C.POINTER(_f32)]),

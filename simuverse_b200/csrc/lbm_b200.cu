@@ -33,6 +33,7 @@ struct IpcPayload {
     int32_t nx, ny, y0, h, pitch;
     uint64_t plane;           // floats
     uint64_t f_off[2];        // byte offsets of f[0], f[1] in the arena
+    uint64_t spare_off;       // byte offset of the third buffer (multi-slab handles; see materialize_prev)
     uint64_t flag_off;        // byte offset of the progress flags
     uint64_t arena_bytes;
     uint64_t local_ptr;       // arena address in the exporting process (same-process attach)
@@ -93,13 +94,17 @@ struct LbmSim {
     uint64_t graph_frame_kernels = 0;
     // two updates per sweep (lbm_fused.cuh)
     FuseGeom fuse{};
-    int *d_fuse_rows = nullptr;            // FuseGeom::row_start
+    int2 *d_fuse_rows = nullptr;           // FuseGeom::items
     unsigned int *d_fuse_flags = nullptr;  // [0] largest armed block_iter seen by k_derive, [1] k_ring_check verdict
     uint8_t *cls_halo = nullptr;           // multi-slab: class rows y0-1 and y0+h (2 * pitch bytes)
     int64_t countdown_left = 0;            // upper bound of the updates during which a force cell may still count down / retire
     bool fuse_blocked = false;             // a ring cell would pull a stale value out of a solid (see k_ring_check)
     bool ring_check_needed = false;
     bool mask_written_since_reset = false;
+    // multi-slab only: a third distribution buffer in the arena (peer-visible), so that the buffer a sweep leaves two
+    // updates behind can be recomputed by an ordinary, neighbour-synchronised update and swapped in
+    float *spare_f = nullptr, *spare_up = nullptr, *spare_dn = nullptr;
+    size_t spare_off = 0;
     bool prev_stale = false;               // after a two-update sweep the non-current buffer holds t, not t+1
     int flip = 0;                          // parity of the buffer-pointer exchanges done by two-update sweeps
     cudaGraphExec_t graph_pairs[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + swap]: kGraphSteps / 2 sweeps
@@ -159,7 +164,8 @@ int derive_rows(LbmSim *s, int l0, int l1) {
         CU(cudaMemcpyAsync(&armed, s->d_fuse_flags, sizeof(armed), cudaMemcpyDeviceToHost, s->stream));
         CU(cudaStreamSynchronize(s->stream));
         // a cell armed with k counts down during k updates and is retired (CLS_FLIPPED) by the one after
-        if (armed) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
+        // (multi-slab: every rank must decide alike, so lbm_write_lattice_info scans the caller's bytes instead)
+        if (armed && s->d.world == 1) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
     }
     if (s->mask_written_since_reset) s->ring_check_needed = true;
     // the mask changed: rebuild the list of warps k_step_vec leaves to k_step_mixed
@@ -296,44 +302,58 @@ int fuse_geometry(LbmSim *s) {
     const int h = s->P.h;
     g.strips = (G + kFuseOut - 1) / kFuseOut;
     g.ctas_x = (g.strips + kFuseWarps - 1) / kFuseWarps;
-    std::vector<int> starts, starts0;
     int fixed = 0, fixed0 = 8;
     if (const char *e = getenv("LBM_FUSE_ROWS")) fixed = atoi(e);   // uniform height (tests, tuning)
     if (const char *e = getenv("LBM_FUSE_ROWS0")) fixed0 = std::max(1, atoi(e));
-    if (fixed > 0) {
-        for (int y = 0; y < h; y += fixed) starts.push_back(y);
-        fixed0 = std::min(fixed0, fixed);
-    } else {
+    int H = fixed;
+    if (H <= 0) {
         int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true>, kFuseThreads, 0);
+        if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true>, kFuseThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false>, kFuseThreads, 0);
         // Uniform height giving at least ~6 waves of CTAs (measured on B200: with fewer the sweep ends in a long
         // tail; 4096^2 is best at 16 rows, 16384^2 at 32), between 8 and 32 rows.
         int h_min = 8, h_max = 32;
         if (const char *e = getenv("LBM_FUSE_HMIN")) h_min = std::max(1, atoi(e));
         if (const char *e = getenv("LBM_FUSE_HMAX")) h_max = std::max(h_min, atoi(e));
         const long long resident = (long long)sms * std::max(per_sm, 1);
-        int H = (int)((long long)h * g.ctas_x / (6 * resident));
+        H = (int)((long long)h * g.ctas_x / (6 * resident));
         H = std::max(h_min, std::min(H, h_max));
-        for (int y = 0; y < h; y += H) starts.push_back(y);
     }
-    g.rowblocks = (int)starts.size();
-    starts.push_back(h);
-    // the first strip column (the inlet column of a channel) in short blocks: see k_frame2
-    for (int y = 0; y < h; y += fixed0) starts0.push_back(y);
-    g.rowblocks0 = (int)starts0.size();
-    starts0.push_back(h);
+    int H0 = std::min(fixed0, H); // the first strip column (the inlet column of a channel) in short blocks: see k_frame2
+    if (s->d.world > 1) { H = std::max(H, 2); H0 = std::max(H0, 2); } // a neighbour reads two rows: one block must hold both
+    // blocks of height `hh` in dispatch order: the one with row 0, the one with row h-1, then the rest top to bottom
+    auto cut = [&](int hh, std::vector<int2> &out) {
+        std::vector<int2> blocks;
+        for (int y = 0; y < h; y += hh) blocks.push_back(make_int2(y, std::min(h, y + hh)));
+        // the last block must hold the last two rows (multi-slab): merge a 1-row remainder into its predecessor
+        if (blocks.size() > 1 && blocks.back().y - blocks.back().x < 2) {
+            blocks[blocks.size() - 2].y = h;
+            blocks.pop_back();
+        }
+        out.push_back(blocks.front());
+        if (blocks.size() > 1) out.push_back(blocks.back());
+        for (size_t k = 1; k + 1 < blocks.size(); k++) out.push_back(blocks[k]);
+        return blocks.size() > 1 ? 2 : 1;
+    };
+    std::vector<int2> items0, items;
+    g.edge0 = cut(H0, items0);
+    g.edge = cut(H, items);
+    g.rowblocks0 = (int)items0.size();
+    g.rowblocks = (int)items.size();
     if (g.ctas_x == 1) { // a single strip column: everything is "column 0"
-        starts0 = starts;
+        items0 = items;
         g.rowblocks0 = g.rowblocks;
+        g.edge0 = g.edge;
         g.rowblocks = 0;
+        g.edge = 0;
+        items.clear();
     }
-    starts0.insert(starts0.end(), starts.begin(), starts.end());
-    starts.swap(starts0);
+    items0.insert(items0.end(), items.begin(), items.end());
     if (s->d_fuse_rows) { cudaFree(s->d_fuse_rows); s->d_fuse_rows = nullptr; }
-    CU(cudaMalloc(&s->d_fuse_rows, sizeof(int) * starts.size()));
-    CU(cudaMemcpy(s->d_fuse_rows, starts.data(), sizeof(int) * starts.size(), cudaMemcpyHostToDevice));
-    g.row_start = s->d_fuse_rows;
+    CU(cudaMalloc(&s->d_fuse_rows, sizeof(int2) * items0.size()));
+    CU(cudaMemcpy(s->d_fuse_rows, items0.data(), sizeof(int2) * items0.size(), cudaMemcpyHostToDevice));
+    g.items = s->d_fuse_rows;
     return LBM_OK;
 }
 
@@ -353,15 +373,22 @@ int run_ring_check(LbmSim *s) {
 // May the next two updates run as one sweep?  (see the header comment of lbm_fused.cuh)
 bool fuse_possible(const LbmSim *s) {
     return !s->aa && !(s->d.flags & (LBM_FLAG_KERNEL_GENERIC | LBM_FLAG_NO_FUSE | LBM_FLAG_MACRO_EVERY_STEP)) &&
-           s->d.world == 1 && (s->P.nx % kFuseCells) == 0 && s->P.h >= 4 && !s->P.macro16 && !s->P.macro32;
+           (s->d.world == 1 || s->attached) && (s->P.nx % kFuseCells) == 0 && s->P.h >= 4 && !s->P.macro16 && !s->P.macro32;
 }
 
 int fuse_eligible(LbmSim *s, bool *ok) {
     *ok = false;
     if (!fuse_possible(s) || s->countdown_left > 0) return LBM_OK;
     if (s->ring_check_needed) {
-        int rc = run_ring_check(s);
-        if (rc) return rc;
+        if (s->d.world > 1) {
+            // the verdict has to be the same on every rank, and k_ring_check only sees this slab: any mask write
+            // or restore after lbm_reset keeps a multi-slab lattice on single updates until the next lbm_reset
+            s->fuse_blocked = true;
+            s->ring_check_needed = false;
+        } else {
+            int rc = run_ring_check(s);
+            if (rc) return rc;
+        }
     }
     *ok = !s->fuse_blocked;
     return LBM_OK;
@@ -376,8 +403,14 @@ int launch_pair(LbmSim *s, int first) {
     const Coef &k = s->P.k;
     const bool symw = k.w[1] == k.w[2] && k.w[1] == k.w[3] && k.w[1] == k.w[4] && k.w[5] == k.w[6] && k.w[5] == k.w[7] &&
                       k.w[5] == k.w[8];
-    if (symw) k_frame2<true><<<(unsigned int)blocks, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-    else k_frame2<false><<<(unsigned int)blocks, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    const unsigned int grid = (unsigned int)blocks;
+    if (s->d.world > 1) {
+        if (symw) k_frame2<true, true><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+        else k_frame2<false, true><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    } else {
+        if (symw) k_frame2<true, false><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+        else k_frame2<false, false><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    }
     int rc = check_launch(s, "k_frame2");
     if (rc) return rc;
     exchange_buffers(s);
@@ -393,6 +426,27 @@ int launch_pair(LbmSim *s, int first) {
 // recomputed: one ordinary update from t into a temporary, copied over the stale buffer.
 int materialize_prev(LbmSim *s) {
     if (!s->prev_stale) return LBM_OK;
+    if (s->d.world > 1) {
+        // Multi-slab: an ordinary update t -> t+1 into the third buffer, synchronised with the neighbour slabs like any
+        // other (COLLECTIVE: every rank gets here through the same read call), then that buffer takes the stale one's place.
+        SlabParams &P = s->P;
+        const int old = s->swap ^ 1;
+        SlabParams Q = P;
+        Q.f[0] = P.f[old]; Q.up[0] = P.up[old]; Q.dn[0] = P.dn[old];
+        Q.f[1] = s->spare_f; Q.up[1] = s->spare_up; Q.dn[1] = s->spare_dn;
+        Q.macro16 = nullptr; Q.macro32 = nullptr;
+        int n = 0;
+        cudaError_t e = launch_step_vec(Q, s->sync, s->mixed, 0, s->stream, &n);
+        if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "recomputing the previous buffer failed: %s", cudaGetErrorString(e));
+        s->launches += n;
+        std::swap(P.f[old], s->spare_f);
+        std::swap(P.up[old], s->spare_up);
+        std::swap(P.dn[old], s->spare_dn);
+        std::swap(s->f_off[old], s->spare_off);
+        invalidate_graphs(s); // buffer pointers are baked into captured launches
+        s->prev_stale = false;
+        return LBM_OK;
+    }
     const SlabParams &P = s->P;
     const int cur = s->swap, old = s->swap ^ 1;
     float *tmp = nullptr;
@@ -540,15 +594,17 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     if (s->aa && d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "LBM_FLAG_AA is single-slab only");
     if (s->aa && (d.flags & LBM_FLAG_KERNEL_GENERIC)) return fail(s, LBM_ERR_UNSUPPORTED, "LBM_FLAG_AA has its own kernels");
     const size_t fbytes = align_up(sizeof(float) * 9 * P.plane, 256);
-    const size_t n_buf = s->aa ? 1 : 2;
+    const size_t n_buf = s->aa ? 1 : (d.world > 1 ? 3 : 2);
     s->f_off[0] = 0;
     s->f_off[1] = s->aa ? 0 : fbytes;
+    s->spare_off = 2 * fbytes;
     s->flag_off = n_buf * fbytes;
     s->arena_bytes = n_buf * fbytes + 256;
     CU(cudaMalloc(&s->arena, s->arena_bytes));
     CU(cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream));
     P.f[0] = reinterpret_cast<float *>(s->arena + s->f_off[0]);
     P.f[1] = reinterpret_cast<float *>(s->arena + s->f_off[1]);
+    if (d.world > 1) s->spare_f = reinterpret_cast<float *>(s->arena + s->spare_off);
     // world == 1: rows -1 / h wrap onto the own rows h-1 / 0 (layout_and_fn.wgsl:45-49)
     for (int b = 0; b < 2; b++) {
         P.up[b] = P.f[b] + (size_t)(P.h - 1) * P.pitch;
@@ -670,6 +726,17 @@ extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const voi
         if (rc) return rc;
     }
     const uint64_t lo = byte_offset, hi = byte_offset + nbytes;
+    if (s->d.world > 1 && byte_offset % sizeof(LatticeInfo) == 0) {
+        // armed force cells anywhere in the write, not only in this slab's rows: all ranks are handed the same
+        // call and must agree on when two updates may run as one sweep
+        const LatticeInfo *cells = static_cast<const LatticeInfo *>(src);
+        int32_t armed = 0;
+        for (uint64_t k = 0; k < nbytes / sizeof(LatticeInfo); k++)
+            if ((cells[k].material == 3 || cells[k].material == 6) && cells[k].block_iter > armed) armed = cells[k].block_iter;
+        if (armed) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
+    }
+    // (multi-slab) whether or not the write touches this slab's rows: all slabs leave the sweeps together
+    if (s->d.world > 1 && s->mask_written_since_reset) s->ring_check_needed = true;
     int touched_lo = P.h + 2, touched_hi = -1; // halo-indexed rows r = 0..h+1
     // (halo-indexed local row range, global first row) of the three pieces this slab keeps
     struct Piece { int r0, rows, gy; };
@@ -723,6 +790,7 @@ extern "C" int lbm_reset(LbmSim *s) {
     k_init<<<grid2d(s->P.nx, s->P.h, block), block, 0, s->stream>>>(s->P);
     int rc = check_launch(s, "k_init");
     if (rc) return rc;
+    if (s->spare_f) CU(cudaMemsetAsync(s->spare_f, 0, sizeof(float) * 9 * s->P.plane, s->stream));
     s->swap = 0;
     s->steps_since_reset = 0;
     s->macro_writes++; // init.wgsl:62 rewrites the texture
@@ -908,6 +976,12 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
 }
 
 extern "C" int lbm_swap_index(const LbmSim *s) { return s ? s->swap : -1; }
+
+extern "C" int lbm_refresh_previous(LbmSim *s) {
+    if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    return materialize_prev(s);
+}
 
 extern "C" int lbm_sync(LbmSim *s) {
     if (!s) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
@@ -1170,6 +1244,7 @@ extern "C" int lbm_ipc_export(LbmSim *s, LbmIpcBlob *out) {
     p.nx = s->P.nx; p.ny = s->P.ny; p.y0 = s->P.y0; p.h = s->P.h; p.pitch = s->P.pitch;
     p.plane = s->P.plane;
     p.f_off[0] = s->f_off[0]; p.f_off[1] = s->f_off[1];
+    p.spare_off = s->spare_off;
     p.flag_off = s->flag_off;
     p.arena_bytes = s->arena_bytes;
     p.local_ptr = (uint64_t)(uintptr_t)s->arena;
@@ -1222,6 +1297,8 @@ extern "C" int lbm_ipc_attach(LbmSim *s, const LbmIpcBlob *up, const LbmIpcBlob 
         P.up[b] = reinterpret_cast<float *>(base[0] + pl[0].f_off[b]) + (size_t)(pl[0].h - 1) * pl[0].pitch;
         P.dn[b] = reinterpret_cast<float *>(base[1] + pl[1].f_off[b]);
     }
+    s->spare_up = reinterpret_cast<float *>(base[0] + pl[0].spare_off) + (size_t)(pl[0].h - 1) * pl[0].pitch;
+    s->spare_dn = reinterpret_cast<float *>(base[1] + pl[1].spare_off);
     P.up_plane = pl[0].plane;
     P.dn_plane = pl[1].plane;
     s->sync.peer_flags[0] = reinterpret_cast<unsigned int *>(base[0] + pl[0].flag_off);

@@ -262,6 +262,10 @@ class D2Q9Node:
         check(lib.lbm_last_step_n_ms(self._h, C.byref(ms)), self._h)
         return ms.value
 
+    def refresh_previous(self):
+        """Recompute the buffer a two-update sweep left two updates behind (collective on multi-slab lattices)."""
+        check(lib.lbm_refresh_previous(self._h), self._h)
+
     @property
     def launch_count(self):
         return int(lib.lbm_launch_count(self._h))

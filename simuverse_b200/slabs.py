@@ -83,9 +83,18 @@ class SlabRank:
         _, up, down = exchange_blobs(self.dist, self.node.ipc_export(), self.group)
         self.node.ipc_attach(up, down)
 
+    def refresh_previous(self):
+        """Collective: after two-update sweeps, bring the non-current buffer back to "one update behind" on every
+        slab (lbm_refresh_previous) and wait until all slabs are done.  Call before reading that buffer or the
+        on-demand macro field."""
+        self.node.refresh_previous()
+        self.barrier()
+
     def gather_distributions(self, which=None):
         """Global (9, ny, nx) distributions on every rank."""
         which = self.node.swap_index if which is None else which
+        if which != self.node.swap_index:
+            self.refresh_previous()
         return gather_rows(self.dist, self.node.read_distributions(which), self.node.lattice[1], self.group)
 
     def barrier(self):
@@ -139,13 +148,24 @@ class SlabGroup:
         self.sync()
 
     def step_n(self, n_steps):
-        # round-robin: a slab's step t waits (on the device) for its neighbours' step t-1
-        for _ in range(n_steps):
+        # round-robin: a slab's launch t waits (on the device) for its neighbours' launch t-1; pairs of updates go
+        # out as one lbm_step_n(2) so that every slab may run them as one two-update sweep
+        for _ in range(n_steps // 2):
+            for n in self.nodes:
+                n.step_n(2)
+        if n_steps % 2:
             for n in self.nodes:
                 n.step_n(1)
 
+    def refresh_previous(self):
+        """After sweeps: recompute the non-current buffer on every slab (collective), then wait for all of them."""
+        for n in self.nodes:
+            n.refresh_previous()
+        self.sync()
+
     def write_lattice_info(self, byte_offset, cells):
         self.sync()
+        self.refresh_previous()
         for n in self.nodes:
             n.write_lattice_info(byte_offset, cells)
         self.sync()
@@ -156,10 +176,13 @@ class SlabGroup:
 
     def read_distributions(self, which):
         self.sync()
+        if which != self.swap_index:
+            self.refresh_previous()
         return np.concatenate([n.read_distributions(which) for n in self.nodes], axis=1)
 
     def read_macro(self):
         self.sync()
+        self.refresh_previous()  # the on-demand field is pulled from the buffer one update back
         return np.concatenate([n.read_macro() for n in self.nodes], axis=1)
 
     def read_lattice_info(self):
