@@ -386,7 +386,8 @@ int run_ring_check(LbmSim *s) {
 // May the next two updates run as one sweep?  (see the header comment of lbm_fused.cuh)
 bool fuse_possible(const LbmSim *s) {
     return !s->aa && !(s->d.flags & (LBM_FLAG_KERNEL_GENERIC | LBM_FLAG_NO_FUSE | LBM_FLAG_MACRO_EVERY_STEP)) &&
-           (s->d.world == 1 || s->attached) && (s->P.nx % kFuseCells) == 0 && s->P.h >= 4 && !s->P.macro16 && !s->P.macro32;
+           (s->d.world == 1 || s->attached) && (s->P.nx % kFuseCells) == 0 &&
+           s->d.ny / s->d.world >= 4 /* the thinnest slab: every rank must answer alike */ && !s->P.macro16 && !s->P.macro32;
 }
 
 int fuse_eligible(LbmSim *s, bool *ok) {
