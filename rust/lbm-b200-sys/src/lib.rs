@@ -145,6 +145,7 @@ unsafe extern "C" {
     pub fn lbm_ipc_attach(sim: *mut LbmSim, up: *const LbmIpcBlob, down: *const LbmIpcBlob) -> c_int;
 
     pub fn lbm_refresh_previous(sim: *mut LbmSim) -> i32;
+    pub fn lbm_sweep_blocks(h: i32, rows_per_block: i32, out: *mut i32, cap: i32, n_edge: *mut i32) -> i32;
     pub fn lbm_launch_count(sim: *const LbmSim) -> u64;
     pub fn lbm_fused_sweep_count(sim: *const LbmSim) -> u64;
     pub fn lbm_last_step_n_ms(sim: *mut LbmSim, ms: *mut f32) -> c_int;

@@ -11,6 +11,7 @@
 //
 // f32 throughout, one rounding per operation (built with -ffp-contract=off), so the masks are
 // bit-identical to what the Rust code computes with glam::Vec2.
+#include <vector>
 #include <cmath>
 #include <cstring>
 
@@ -245,4 +246,31 @@ extern "C" void lbm_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas
             o->fade = 0.0f;
         }
     }
+}
+
+// ------------------------------------------------------------------ work items of a two-update sweep
+// Cuts rows [0, h) into blocks of `rows_per_block` rows in DISPATCH order: the block with row 0, the block with row
+// h-1, then the rest top to bottom (on a multi-slab lattice the first two are the ones that talk to the neighbour
+// slabs, lbm_fused.cuh).  A 1-row remainder is merged into its predecessor, so that the last block always holds
+// the slab's last two rows.  out: (y0, y1) pairs; returns the number of blocks, *n_edge = 1 or 2.
+extern "C" int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_t cap, int32_t *n_edge) {
+    if (h < 1 || rows_per_block < 1 || !out) return 0;
+    std::vector<int32_t> lo_, hi_;
+    for (int32_t y = 0; y < h; y += rows_per_block) {
+        lo_.push_back(y);
+        hi_.push_back(y + rows_per_block < h ? y + rows_per_block : h);
+    }
+    if (lo_.size() > 1 && hi_.back() - lo_.back() < 2) {
+        lo_.pop_back();
+        hi_.pop_back();
+        hi_.back() = h;
+    }
+    const int32_t n = (int32_t)lo_.size();
+    if (n > cap) return 0;
+    int32_t k = 0;
+    out[2 * k] = lo_.front(); out[2 * k + 1] = hi_.front(); k++;
+    if (n > 1) { out[2 * k] = lo_.back(); out[2 * k + 1] = hi_.back(); k++; }
+    for (int32_t i = 1; i + 1 < n; i++) { out[2 * k] = lo_[i]; out[2 * k + 1] = hi_[i]; k++; }
+    if (n_edge) *n_edge = n > 1 ? 2 : 1;
+    return n;
 }

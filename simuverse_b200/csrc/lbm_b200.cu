@@ -335,19 +335,13 @@ int fuse_geometry(LbmSim *s) {
     }
     int H0 = std::min(fixed0, H); // the first strip column (the inlet column of a channel) in short blocks: see k_frame2
     if (s->d.world > 1) { H = std::max(H, 2); H0 = std::max(H0, 2); } // a neighbour reads two rows: one block must hold both
-    // blocks of height `hh` in dispatch order: the one with row 0, the one with row h-1, then the rest top to bottom
+    // blocks of height `hh` in dispatch order (lbm_sweep_blocks, host_logic.cpp)
     auto cut = [&](int hh, std::vector<int2> &out) {
-        std::vector<int2> blocks;
-        for (int y = 0; y < h; y += hh) blocks.push_back(make_int2(y, std::min(h, y + hh)));
-        // the last block must hold the last two rows (multi-slab): merge a 1-row remainder into its predecessor
-        if (blocks.size() > 1 && blocks.back().y - blocks.back().x < 2) {
-            blocks[blocks.size() - 2].y = h;
-            blocks.pop_back();
-        }
-        out.push_back(blocks.front());
-        if (blocks.size() > 1) out.push_back(blocks.back());
-        for (size_t k = 1; k + 1 < blocks.size(); k++) out.push_back(blocks[k]);
-        return blocks.size() > 1 ? 2 : 1;
+        std::vector<int32_t> flat(2 * ((size_t)h / std::max(hh, 1) + 2));
+        int32_t n_edge = 0;
+        const int n = lbm_sweep_blocks(h, hh, flat.data(), (int32_t)(flat.size() / 2), &n_edge);
+        for (int k = 0; k < n; k++) out.push_back(make_int2(flat[2 * k], flat[2 * k + 1]));
+        return (int)n_edge;
     };
     std::vector<int2> items0, items;
     g.edge0 = cut(H0, items0);

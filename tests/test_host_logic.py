@@ -171,3 +171,29 @@ def test_cpp_host_mirror_compiles_and_runs(tmp_path):
                            "-Wl,-rpath," + os.path.dirname(sb.LIB_PATH), "-o", str(exe)])
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "HOST_MIRROR_OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("h,rows", [(4096, 16), (2048, 31), (45, 1), (45, 2), (45, 64), (33, 8), (4, 8), (17, 16), (5, 2)])
+def test_sweep_row_blocks_cover_every_row_once(h, rows):
+    """Work items of the two-update sweep (lbm_sweep_blocks): a partition of [0, h) in dispatch order with the
+    blocks holding the first and the last rows up front, and a last block of at least two rows."""
+    import ctypes as C
+
+    from simuverse_b200._capi import lib
+
+    cap = h // rows + 2
+    out = (C.c_int32 * (2 * cap))()
+    n_edge = C.c_int32(0)
+    n = lib.lbm_sweep_blocks(h, rows, out, cap, C.byref(n_edge))
+    assert n >= 1
+    blocks = [(out[2 * k], out[2 * k + 1]) for k in range(n)]
+    covered = sorted(blocks)
+    assert covered[0][0] == 0 and covered[-1][1] == h
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:])), "blocks must tile the rows without gaps"
+    assert all(y1 > y0 for y0, y1 in blocks)
+    assert blocks[0][0] == 0
+    assert n_edge.value == (2 if n > 1 else 1)
+    if n > 1:
+        assert blocks[1][1] == h and blocks[1][1] - blocks[1][0] >= 2 or h < 2
+        assert [b for b in blocks[2:]] == covered[1:-1], "interior blocks top to bottom"
+    assert lib.lbm_sweep_blocks(h, rows, out, 0, C.byref(n_edge)) == 0  # cap too small: refused, nothing written
