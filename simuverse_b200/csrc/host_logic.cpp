@@ -195,7 +195,12 @@ extern "C" uint64_t lbm_external_force_cells(int32_t nx, int32_t ny, uint32_t la
     if (force > 0.12f) force = 0.12f;
     const float angle = std::atan2(pos.y - pre.y, pos.x - pre.x);
     const LatticeInfo forced{LATTICE_EXTERNAL_FORCE, 90, force * std::cos(angle), force * std::sin(angle)};
+    // d2q9_node.rs:277 divides by lattice_pixel_size - 1.  With lattice_pixel_size == 1 (scale_factor <= 0.5) that is a
+    // division by zero: c = +inf saturates to i32::MAX and the reference walks ~2^31 sample points.  Deliberate
+    // deviation: a library entry point must not stall, so such a drag produces no force cells.
+    if (lattice_pixel_size < 2) return 0;
     const float c = std::ceil(dis / static_cast<float>(lattice_pixel_size - 1));
+    if (!std::isfinite(c)) return 0;
     const float step = dis / c;
     uint64_t n = 0;
     const int32_t count = as_i32(c);

@@ -101,6 +101,19 @@ struct LbmSim {
     bool fuse_blocked = false;             // a ring cell would pull a stale value out of a solid (see k_ring_check)
     bool ring_check_needed = false;
     bool mask_written_since_reset = false;
+    bool mixed_dirty = false;              // the mask changed: the mixed-warp list is rebuilt before the next single update
+    bool halo_retire_pending = false;      // multi-slab: armed force cells in the info halo rows retire when the countdown ends
+    // pinned staging ring of lbm_write_lattice_info: the caller's bytes are copied here and travel asynchronously, so
+    // a mask write never waits for the device (and the caller may reuse its buffer at once)
+    static constexpr int kStageSlots = 4;
+    static constexpr size_t kStageBytes = 4u << 20;
+    char *stage[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool stage_used[kStageSlots] = {false, false, false, false};
+    int stage_next = 0;
+    size_t stage_cursor = 0;
+    float *prev_spare = nullptr;           // single slab: persistent spare buffer of materialize_prev (allocated on first use)
+    bool spare_keep_dirty = true;          // the slots no update writes may differ between the spare and the real buffers
     // multi-slab only: a third distribution buffer in the arena (peer-visible), so that the buffer a sweep leaves two
     // updates behind can be recomputed by an ordinary, neighbour-synchronised update and swapped in
     float *spare_f = nullptr, *spare_up = nullptr, *spare_dn = nullptr;
@@ -109,6 +122,11 @@ struct LbmSim {
     int flip = 0;                          // parity of the buffer-pointer exchanges done by two-update sweeps
     cudaGraphExec_t graph_pairs[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + swap]: kGraphSteps / 2 sweeps
     uint64_t graph_pairs_kernels[4] = {0, 0, 0, 0};
+    // frames with tracer particles as sweeps: the texture update 1 of a sweep stores into, and graphs of TWO frames
+    // (sweep, particles(t+1), particles(t+2)) x 2 — an even number of sweeps leaves the buffer pointers unchanged
+    __half *macro_mid = nullptr;
+    cudaGraphExec_t graph_pframes[2] = {nullptr, nullptr}; // [flip]
+    uint64_t graph_pframes_kernels[2] = {0, 0};
     uint64_t fused_sweeps = 0;
     std::string err;
 };
@@ -145,42 +163,46 @@ int check_launch(LbmSim *s, const char *what) {
 dim3 grid2d(int nx, int rows, dim3 block) { return dim3((nx + block.x - 1) / block.x, (rows + block.y - 1) / block.y, 1); }
 
 void invalidate_graphs(LbmSim *s);
+void invalidate_step_graphs(LbmSim *s);
 
-int derive_rows(LbmSim *s, int l0, int l1) {
+// Re-derives the class / neighbour planes of owned rows [l0, l1) from the info buffer.  Asynchronous: nothing is read
+// back here.  The mixed-warp list of the single-update kernels is rebuilt lazily (ensure_mixed), and only the graphs
+// that contain those kernels are dropped — a two-update sweep does not depend on the mask geometry.
+// want_armed: also collect the largest armed block_iter of the rows into d_fuse_flags[0] (read by the caller).
+int derive_rows(LbmSim *s, int l0, int l1, bool want_armed = false) {
     l0 = std::max(l0, 0);
     l1 = std::min(l1, s->P.h);
     if (l0 >= l1) return LBM_OK;
     dim3 block(64, 4);
-    CU(cudaMemsetAsync(s->d_fuse_flags, 0, sizeof(unsigned int), s->stream));
-    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, s->d_fuse_flags);
+    if (want_armed) CU(cudaMemsetAsync(s->d_fuse_flags, 0, sizeof(unsigned int), s->stream));
+    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, want_armed ? s->d_fuse_flags : nullptr);
     int rc = check_launch(s, "k_derive");
     if (rc) return rc;
     if (s->cls_halo) {
         k_derive_halo<<<(s->P.pitch + 255) / 256, 256, 0, s->stream>>>(s->P, s->cls_halo, s->cls_halo + s->P.pitch);
         if ((rc = check_launch(s, "k_derive_halo"))) return rc;
     }
-    {
-        unsigned int armed = 0;
-        CU(cudaMemcpyAsync(&armed, s->d_fuse_flags, sizeof(armed), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        // a cell armed with k counts down during k updates and is retired (CLS_FLIPPED) by the one after
-        // (multi-slab: every rank must decide alike, so lbm_write_lattice_info scans the caller's bytes instead)
-        if (armed && s->d.world == 1) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
-    }
-    if (s->mask_written_since_reset) s->ring_check_needed = true;
-    // the mask changed: rebuild the list of warps k_step_vec leaves to k_step_mixed
+    s->mixed_dirty = true;
+    invalidate_step_graphs(s); // launch geometry of the single-update kernels is baked into those graphs
+    return LBM_OK;
+}
+
+// The list of warps k_step_vec leaves to k_step_mixed, rebuilt after a mask change — before the next single update, not
+// at the mask write (one full pass over the class plane and a device -> host count).
+int ensure_mixed(LbmSim *s) {
+    if (!s->mixed_dirty) return LBM_OK;
+    s->mixed_dirty = false;
     MixedList &M = s->mixed;
-    if (M.total > 0) {
-        CU(cudaMemsetAsync(M.count_dev, 0, sizeof(uint32_t), s->stream));
-        k_scan_mixed<<<(M.total + 255) / 256, 256, 0, s->stream>>>(s->P, M.list, M.count_dev, M.warps_per_row);
-        if ((rc = check_launch(s, "k_scan_mixed"))) return rc;
-        CU(cudaMemcpyAsync(&M.count, M.count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        M.everywhere = M.count > M.total / 2;
-        // few mixed warps, or a lattice so small that a second launch costs more than a few slow threads
-        M.rare = M.count <= M.total / 8 || M.total <= 8192;
-    }
-    invalidate_graphs(s); // launch geometry is baked into captured graphs
+    if (M.total == 0 || s->aa || (s->d.flags & LBM_FLAG_KERNEL_GENERIC)) return LBM_OK;
+    CU(cudaMemsetAsync(M.count_dev, 0, sizeof(uint32_t), s->stream));
+    k_scan_mixed<<<(M.total + 255) / 256, 256, 0, s->stream>>>(s->P, M.list, M.count_dev, M.warps_per_row);
+    int rc = check_launch(s, "k_scan_mixed");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(&M.count, M.count_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    M.everywhere = M.count > M.total / 2;
+    // few mixed warps, or a lattice so small that a second launch costs more than a few slow threads
+    M.rare = M.count <= M.total / 8 || M.total <= 8192;
     return LBM_OK;
 }
 
@@ -263,19 +285,29 @@ int aa_canonical(LbmSim *s) {
 
 constexpr int kGraphSteps = 16;
 
-void invalidate_graphs(LbmSim *s) {
+// graphs that contain k_step_vec / k_step_mixed launches (their geometry follows the mask)
+void invalidate_step_graphs(LbmSim *s) {
     for (auto &g : s->graph_steps)
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     if (s->graph_frame) { cudaGraphExecDestroy(s->graph_frame); s->graph_frame = nullptr; }
+}
+
+void invalidate_graphs(LbmSim *s) {
+    invalidate_step_graphs(s);
     for (auto &g : s->graph_pairs)
+        if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto &g : s->graph_pframes)
         if (g) { cudaGraphExecDestroy(g); g = nullptr; }
 }
 
 // (multi-slab launches are replayable too: the step counter the edge CTAs compare against lives on the device)
 bool graphs_enabled(const LbmSim *s) { return !(s->d.flags & LBM_FLAG_NO_GRAPH); }
 
-int launch_particles(LbmSim *s) {
-    cudaError_t e = launch_particle_update(s->P, s->field, s->pu, s->particles, s->canvas, s->stream);
+// tex: the macro texture to sample (nullptr = the one the latest update wrote)
+int launch_particles(LbmSim *s, const __half *tex = nullptr) {
+    SlabParams Q = s->P;
+    if (tex) Q.macro16 = const_cast<__half *>(tex);
+    cudaError_t e = launch_particle_update(Q, s->field, s->pu, s->particles, s->canvas, s->stream);
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_particle_update failed: %s", cudaGetErrorString(e));
     s->launches++;
     return LBM_OK;
@@ -309,8 +341,8 @@ int fuse_geometry(LbmSim *s) {
     if (H <= 0) {
         int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true>, kFuseThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false>, kFuseThreads, 0);
+        if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true, 0>, kFuseThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false, 0>, kFuseThreads, 0);
         // Uniform height giving at least ~6 waves of CTAs (measured on B200: with fewer the sweep ends in a long
         // tail; 4096^2 is best at 16 rows, 16384^2 at 32), between 8 and 32 rows.
         int h_min = 8, h_max = 32;
@@ -361,6 +393,7 @@ int fuse_geometry(LbmSim *s) {
     CU(cudaMalloc(&s->d_fuse_rows, sizeof(int2) * items0.size()));
     CU(cudaMemcpy(s->d_fuse_rows, items0.data(), sizeof(int2) * items0.size(), cudaMemcpyHostToDevice));
     g.items = s->d_fuse_rows;
+    g.negzero2 = 0x8000000080000000ull;
     return LBM_OK;
 }
 
@@ -377,20 +410,41 @@ int run_ring_check(LbmSim *s) {
     return LBM_OK;
 }
 
+// The sweep finds the values the per-direction clamp changes by an unsigned compare of bit patterns against max_i
+// (collide2): that needs every max_i to be >= +0 and not NaN.  Anything else takes the single-update kernels.
+bool clamp_limits_ordinary(const Coef &k) {
+    for (int i = 0; i < 9; i++) {
+        uint32_t b;
+        memcpy(&b, &k.mx[i], sizeof(b));
+        if (b > 0x7f800000u) return false;
+    }
+    return true;
+}
+
 // May the next two updates run as one sweep?  (see the header comment of lbm_fused.cuh)
 bool fuse_possible(const LbmSim *s) {
-    return !s->aa && !(s->d.flags & (LBM_FLAG_KERNEL_GENERIC | LBM_FLAG_NO_FUSE | LBM_FLAG_MACRO_EVERY_STEP)) &&
+    return !s->aa && clamp_limits_ordinary(s->P.k) && !(s->d.flags & (LBM_FLAG_KERNEL_GENERIC | LBM_FLAG_NO_FUSE)) &&
            (s->d.world == 1 || s->attached) && (s->P.nx % kFuseCells) == 0 &&
-           s->d.ny / s->d.world >= 4 /* the thinnest slab: every rank must answer alike */ && !s->P.macro16 && !s->P.macro32;
+           s->d.ny / s->d.world >= 4 /* the thinnest slab: every rank must answer alike */ && !s->P.macro32;
 }
 
 int fuse_eligible(LbmSim *s, bool *ok) {
     *ok = false;
     if (!fuse_possible(s) || s->countdown_left > 0) return LBM_OK;
+    if (s->halo_retire_pending) {
+        // Multi-slab: every armed force cell has finished its countdown by now, in the rows that own them.  The copies
+        // in the info halo rows (read by the edge row blocks of a sweep) follow: material 1, like collide_stream.wgsl:58-60.
+        k_retire_halo<<<(s->P.nx + 255) / 256, 256, 0, s->stream>>>(s->P, 0);
+        int rc = check_launch(s, "k_retire_halo");
+        if (rc) return rc;
+        k_derive_halo<<<(s->P.pitch + 255) / 256, 256, 0, s->stream>>>(s->P, s->cls_halo, s->cls_halo + s->P.pitch);
+        if ((rc = check_launch(s, "k_derive_halo"))) return rc;
+        s->halo_retire_pending = false;
+    }
     if (s->ring_check_needed) {
         if (s->d.world > 1) {
-            // the verdict has to be the same on every rank, and k_ring_check only sees this slab: any mask write
-            // or restore after lbm_reset keeps a multi-slab lattice on single updates until the next lbm_reset
+            // the verdict has to be the same on every rank, and k_ring_check only sees this slab: a write that puts a
+            // solid next to the outer ring (or a restore) keeps a multi-slab lattice on single updates until lbm_reset
             s->fuse_blocked = true;
             s->ring_check_needed = false;
         } else {
@@ -402,22 +456,38 @@ int fuse_eligible(LbmSim *s, bool *ok) {
     return LBM_OK;
 }
 
-// Two updates starting from buffer `first`: ONE launch, then the pointer exchange.
-int launch_pair(LbmSim *s, int first) {
+template <bool SYMW, bool SLABS>
+void launch_frame2(const LbmSim *s, unsigned int grid, int first, int macro) {
+    const FuseGeom &g = s->fuse;
+    if (macro == 2) k_frame2<SYMW, SLABS, 2><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    else if (macro == 1) k_frame2<SYMW, SLABS, 1><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    else k_frame2<SYMW, SLABS, 0><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+}
+
+// Two updates starting from buffer `first`: ONE launch, then the pointer exchange.  With a macro texture the sweep
+// stores the field of t+2 into it; mid_texture: also the field of t+1 into s->macro_mid (frames with tracer particles).
+int launch_pair(LbmSim *s, int first, bool mid_texture = false) {
     const FuseGeom &g = s->fuse;
     const long long blocks = (long long)g.rowblocks0 + (long long)g.rowblocks * (g.ctas_x - 1);
     if (blocks > 2147483647ll) return fail(s, LBM_ERR_INVALID_ARG, "lattice too large for one sweep launch");
     // rho * w is shared between the directions of equal weight when the uploaded weights allow it
     const Coef &k = s->P.k;
-    const bool symw = k.w[1] == k.w[2] && k.w[1] == k.w[3] && k.w[1] == k.w[4] && k.w[5] == k.w[6] && k.w[5] == k.w[7] &&
-                      k.w[5] == k.w[8];
+    auto same4 = [](const float *a) { return a[0] == a[1] && a[0] == a[2] && a[0] == a[3]; };
+    // (also the per-direction limits: the sweep tests the largest value of each class against one limit)
+    const bool symw = same4(k.w + 1) && same4(k.w + 5) && same4(k.mx + 1) && same4(k.mx + 5);
     const unsigned int grid = (unsigned int)blocks;
+    int macro = s->P.macro16 ? 1 : 0;
+    if (mid_texture) {
+        if (!s->P.macro16 || !s->macro_mid) return fail(s, LBM_ERR_STATE, "sweep with a mid-frame texture on a handle without macro textures");
+        macro = 2;
+    }
+    s->P.macro16_mid = s->macro_mid;
     if (s->d.world > 1) {
-        if (symw) k_frame2<true, true><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-        else k_frame2<false, true><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+        if (symw) launch_frame2<true, true>(s, grid, first, macro);
+        else launch_frame2<false, true>(s, grid, first, macro);
     } else {
-        if (symw) k_frame2<true, false><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-        else k_frame2<false, false><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+        if (symw) launch_frame2<true, false>(s, grid, first, macro);
+        else launch_frame2<false, false>(s, grid, first, macro);
     }
     int rc = check_launch(s, "k_frame2");
     if (rc) return rc;
@@ -434,6 +504,10 @@ int launch_pair(LbmSim *s, int first) {
 // recomputed: one ordinary update from t into a temporary, copied over the stale buffer.
 int materialize_prev(LbmSim *s) {
     if (!s->prev_stale) return LBM_OK;
+    {
+        int rc = ensure_mixed(s);
+        if (rc) return rc;
+    }
     if (s->d.world > 1) {
         // Multi-slab: an ordinary update t -> t+1 into the third buffer, synchronised with the neighbour slabs like any
         // other (COLLECTIVE: every rank gets here through the same read call), then that buffer takes the stale one's place.
@@ -455,25 +529,34 @@ int materialize_prev(LbmSim *s) {
         s->prev_stale = false;
         return LBM_OK;
     }
-    const SlabParams &P = s->P;
-    const int cur = s->swap, old = s->swap ^ 1;
-    float *tmp = nullptr;
+    // Single slab: the same, into a spare buffer this handle keeps from its first use on (no allocation, copy or
+    // host synchronisation per call), then the pointers are exchanged.
+    SlabParams &P = s->P;
+    const int old = s->swap ^ 1;
     const size_t bytes = sizeof(float) * 9 * P.plane;
-    CU(cudaMalloc(&tmp, bytes));
-    cudaError_t e = cudaMemsetAsync(tmp, 0, bytes, s->stream);
+    if (!s->prev_spare) {
+        CU(cudaMalloc(&s->prev_spare, bytes));
+        CU(cudaMemsetAsync(s->prev_spare, 0, bytes, s->stream));
+    }
+    // Slots no update ever writes (a solid cell's live slot whose reader sits on the outer ring, boundary.wgsl:19)
+    // are constants of a buffer: the spare — a former state buffer — already holds them unless the lattice was
+    // reset / restored or a solid was painted next to the ring since; only then is the stale buffer copied first.
     SlabParams Q = P;
     Q.f[0] = P.f[old]; Q.up[0] = P.up[old]; Q.dn[0] = P.dn[old];
-    Q.f[1] = tmp; Q.up[1] = tmp + (size_t)(P.h - 1) * P.pitch; Q.dn[1] = tmp;
+    Q.f[1] = s->prev_spare; Q.up[1] = s->prev_spare + (size_t)(P.h - 1) * P.pitch; Q.dn[1] = s->prev_spare;
     Q.macro16 = nullptr; Q.macro32 = nullptr;
     int n = 0;
+    cudaError_t e = cudaSuccess;
+    if (s->spare_keep_dirty) e = cudaMemcpyAsync(s->prev_spare, P.f[old], bytes, cudaMemcpyDeviceToDevice, s->stream);
+    s->spare_keep_dirty = false;
     if (e == cudaSuccess) e = launch_step_vec(Q, s->sync, s->mixed, 0, s->stream, &n);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(P.f[old], tmp, bytes, cudaMemcpyDeviceToDevice, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(tmp);
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "recomputing the previous buffer failed: %s", cudaGetErrorString(e));
     s->launches += n;
+    std::swap(P.f[old], s->prev_spare);
+    P.up[old] = P.f[old] + (size_t)(P.h - 1) * P.pitch;
+    P.dn[old] = P.f[old];
+    invalidate_graphs(s); // buffer pointers are baked into captured launches
     s->prev_stale = false;
-    (void)cur;
     return LBM_OK;
 }
 
@@ -545,6 +628,10 @@ extern "C" void lbm_destroy(LbmSim *s) {
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     cudaFree(s->macro_buf[0] ? s->macro_buf[0] : s->P.macro16);
     cudaFree(s->macro_buf[1]);
+    cudaFree(s->macro_mid);
+    cudaFree(s->prev_spare);
+    for (auto p : s->stage) if (p) cudaFreeHost(p);
+    for (auto e : s->stage_ev) if (e) cudaEventDestroy(e);
     if (s->ev_ready) cudaEventDestroy(s->ev_ready);
     for (auto e : s->ev_copied) if (e) cudaEventDestroy(e);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -696,6 +783,13 @@ extern "C" int lbm_write_uniform(LbmSim *s, const LbmUniform *u) {
     if (!s || !u) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
     if (!uniform_is_d2q9(u))
         return fail(s, LBM_ERR_UNSUPPORTED, "LbmUniform e_w_max / inversed_direction are not the D2Q9 set of fluid/mod.rs:39-52");
+    if (s->prev_stale && s->have_uniform && s->have_info) {
+        // the buffer one update back (and the on-demand field pulled from it) was produced with the OLD coefficients in
+        // the reference: recompute it before they are replaced (collective on a multi-slab lattice)
+        CU(cudaSetDevice(s->device));
+        int rc = materialize_prev(s);
+        if (rc) return rc;
+    }
     s->u = *u;
     s->P.k.omega = u->omega;
     s->P.k.fluid_ty = u->fluid_ty;
@@ -718,6 +812,61 @@ extern "C" int lbm_write_field_uniform(LbmSim *s, const FieldUniform *f) {
     return LBM_OK;
 }
 
+namespace {
+
+// What the bytes of a mask write mean for the step schedule, found on the host from the caller's buffer (so that no
+// device round trip is needed, and so that every rank of a multi-slab lattice — all are handed the same call —
+// reaches the same verdict):
+//   armed        largest block_iter > 0 of an inlet / force cell: single updates while it counts down
+//   border_solid a solid within one cell of the outer ring.  Only there can a solid painted over live fluid leave a
+//                value that a ring cell keeps pulling (boundary.wgsl:19 never rewrites those slots): the sweeps assume 0
+//                (k_ring_check decides), and the buffer one update back must then be the reference's, not a stale one.
+struct WriteScan { int32_t armed; bool border_solid; };
+
+WriteScan scan_written_cells(int nx, int ny, uint64_t byte_offset, const void *src, uint64_t nbytes) {
+    WriteScan w{0, false};
+    const LatticeInfo *cells = static_cast<const LatticeInfo *>(src);
+    const uint64_t n = nbytes / sizeof(LatticeInfo);
+    uint64_t idx = byte_offset / sizeof(LatticeInfo);
+    int x = (int)(idx % (uint64_t)nx), y = (int)(idx / (uint64_t)nx);
+    for (uint64_t k = 0; k < n; k++) {
+        const int m = cells[k].material;
+        if ((m == 3 || m == 6) && cells[k].block_iter > w.armed) w.armed = cells[k].block_iter;
+        if ((m == 2 || m == 4) && (x <= 1 || x >= nx - 2 || y <= 1 || y >= ny - 2)) w.border_solid = true;
+        if (++x == nx) { x = 0; y++; }
+    }
+    return w;
+}
+
+// Host bytes -> device through the pinned staging ring; returns without waiting for the device.  Small writes share
+// a slot (16-byte writes of a drag: one memcpy + one cudaMemcpyAsync each); a slot is reused only after the copies
+// that read it have run (event recorded when the ring moves on).
+int staged_upload(LbmSim *s, char *dst, const char *src, uint64_t nbytes) {
+    while (nbytes > 0) {
+        int k = s->stage_next;
+        if (s->stage_cursor >= LbmSim::kStageBytes) { // slot full: close it, move on
+            CU(cudaEventRecord(s->stage_ev[k], s->stream));
+            s->stage_used[k] = true;
+            k = s->stage_next = (k + 1) % LbmSim::kStageSlots;
+            s->stage_cursor = 0;
+            if (s->stage_used[k]) CU(cudaEventSynchronize(s->stage_ev[k]));
+        }
+        if (!s->stage[k]) {
+            CU(cudaMallocHost(&s->stage[k], LbmSim::kStageBytes));
+            CU(cudaEventCreateWithFlags(&s->stage_ev[k], cudaEventDisableTiming));
+        }
+        const size_t chunk = (size_t)std::min<uint64_t>(nbytes, LbmSim::kStageBytes - s->stage_cursor);
+        char *stage = s->stage[k] + s->stage_cursor;
+        memcpy(stage, src, chunk);
+        CU(cudaMemcpyAsync(dst, stage, chunk, cudaMemcpyHostToDevice, s->stream));
+        s->stage_cursor += (chunk + 15) & ~(size_t)15;
+        dst += chunk; src += chunk; nbytes -= chunk;
+    }
+    return LBM_OK;
+}
+
+}  // namespace
+
 extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const void *src, uint64_t nbytes) {
     if (!s || (!src && nbytes)) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
     const SlabParams &P = s->P;
@@ -728,23 +877,26 @@ extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const voi
                     (unsigned long long)nbytes, (unsigned long long)byte_offset, (unsigned long long)total);
     if (nbytes == 0) return LBM_OK;
     CU(cudaSetDevice(s->device));
-    {   // a solid painted over live fluid keeps that cell's values in BOTH buffers (ring cells may pull them for
-        // ever): the buffer that is not current must hold what the reference holds there, not the state of t-2
+    // Cost: O(bytes written) on the host, asynchronous on the device (d2q9_node.rs:298 issues one 16-byte write per
+    // sample point of a drag; fluid_simulator.rs:158-173).
+    const bool aligned = byte_offset % sizeof(LatticeInfo) == 0 && nbytes % sizeof(LatticeInfo) == 0;
+    WriteScan w{0, true};
+    if (aligned) w = scan_written_cells(P.nx, P.ny, byte_offset, src, nbytes);
+    if (s->mask_written_since_reset && w.border_solid) {
+        // a solid painted over live fluid next to the ring keeps that cell's values in BOTH buffers (ring cells may
+        // pull them for ever): the buffer that is not current must hold what the reference holds there, not the
+        // state of t-2 a sweep left (COLLECTIVE on a multi-slab lattice: every rank sees the same bytes)
         int rc = materialize_prev(s);
         if (rc) return rc;
+        s->ring_check_needed = true;
+        s->spare_keep_dirty = true;
     }
+    if (w.armed > 0) {
+        s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)w.armed + 1);
+        if (s->d.world > 1) s->halo_retire_pending = true;
+    }
+    if (!aligned && s->d.world > 1) s->fuse_blocked = true; // cannot be judged alike on every rank: single updates until lbm_reset
     const uint64_t lo = byte_offset, hi = byte_offset + nbytes;
-    if (s->d.world > 1 && byte_offset % sizeof(LatticeInfo) == 0) {
-        // armed force cells anywhere in the write, not only in this slab's rows: all ranks are handed the same
-        // call and must agree on when two updates may run as one sweep
-        const LatticeInfo *cells = static_cast<const LatticeInfo *>(src);
-        int32_t armed = 0;
-        for (uint64_t k = 0; k < nbytes / sizeof(LatticeInfo); k++)
-            if ((cells[k].material == 3 || cells[k].material == 6) && cells[k].block_iter > armed) armed = cells[k].block_iter;
-        if (armed) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
-    }
-    // (multi-slab) whether or not the write touches this slab's rows: all slabs leave the sweeps together
-    if (s->d.world > 1 && s->mask_written_since_reset) s->ring_check_needed = true;
     int touched_lo = P.h + 2, touched_hi = -1; // halo-indexed rows r = 0..h+1
     // (halo-indexed local row range, global first row) of the three pieces this slab keeps
     struct Piece { int r0, rows, gy; };
@@ -758,17 +910,22 @@ extern "C" int lbm_write_lattice_info(LbmSim *s, uint64_t byte_offset, const voi
         const uint64_t a = std::max(lo, g0), b = std::min(hi, g1);
         if (a >= b) continue;
         char *dst = reinterpret_cast<char *>(P.info) + (uint64_t)pc.r0 * row_bytes + (a - g0);
-        CU(cudaMemcpyAsync(dst, static_cast<const char *>(src) + (a - lo), b - a, cudaMemcpyHostToDevice, s->stream));
+        int rc = staged_upload(s, dst, static_cast<const char *>(src) + (a - lo), b - a);
+        if (rc) return rc;
         touched_lo = std::min(touched_lo, pc.r0 + (int)((a - g0) / row_bytes));
         touched_hi = std::max(touched_hi, pc.r0 + (int)((b - 1 - g0) / row_bytes));
     }
-    // the source may be pageable host memory the caller reuses right away
-    CU(cudaStreamSynchronize(s->stream));
     if (touched_hi >= 0) {
         s->have_info = true;
         // owned row l = r - 1; a changed row alters the neighbour bits of rows l-1 .. l+1
-        int rc = derive_rows(s, touched_lo - 2, touched_hi + 1);
+        int rc = derive_rows(s, touched_lo - 2, touched_hi + 1, !aligned && s->d.world == 1);
         if (rc) return rc;
+        if (!aligned && s->d.world == 1) { // the cells cannot be parsed on the host: ask the device what is armed
+            unsigned int armed = 0;
+            CU(cudaMemcpyAsync(&armed, s->d_fuse_flags, sizeof(armed), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            if (armed) s->countdown_left = std::max<int64_t>(s->countdown_left, (int64_t)armed + 1);
+        }
     }
     return LBM_OK;
 }
@@ -799,6 +956,12 @@ extern "C" int lbm_reset(LbmSim *s) {
     int rc = check_launch(s, "k_init");
     if (rc) return rc;
     if (s->spare_f) CU(cudaMemsetAsync(s->spare_f, 0, sizeof(float) * 9 * s->P.plane, s->stream));
+    if (s->d.world > 1) { // the neighbours' k_init retires armed force cells of rows y0-1 / y0+h (init.wgsl:51-59): so do the copies
+        k_retire_halo<<<(s->P.nx + 255) / 256, 256, 0, s->stream>>>(s->P, 1);
+        if ((rc = check_launch(s, "k_retire_halo"))) return rc;
+    }
+    s->halo_retire_pending = false;
+    s->spare_keep_dirty = true;
     s->swap = 0;
     s->steps_since_reset = 0;
     s->macro_writes++; // init.wgsl:62 rewrites the texture
@@ -822,6 +985,7 @@ extern "C" int lbm_step(LbmSim *s, int32_t swap_index) {
     if (s->aa && swap_index != s->swap)
         return fail(s, LBM_ERR_STATE, "in-place (AA) state is in layout %d: the next step must use swap_index %d", s->swap, s->swap);
     CU(cudaSetDevice(s->device));
+    if ((rc = ensure_mixed(s))) return rc;
     if (swap_index != s->swap && (rc = materialize_prev(s))) return rc; // stepping from the previous buffer
     rc = launch_step(s, swap_index);
     if (rc) return rc;
@@ -859,6 +1023,11 @@ extern "C" int lbm_step_n(LbmSim *s, int32_t n) {
     CU(cudaSetDevice(s->device));
     int left = n;
     const bool graphs = graphs_enabled(s) && n >= 2 * kGraphSteps;
+    {   // a run of sweeps needs no mixed-warp list; anything that may fall back to single updates does
+        bool fz = false;
+        if ((rc = fuse_eligible(s, &fz))) return rc;
+        if ((!fz || (n & 1)) && (rc = ensure_mixed(s))) return rc;
+    }
     // decide and capture before the timed region starts (the common case: nothing is counting down)
     bool fused = false;
     if (left >= 2 && s->countdown_left == 0) {
@@ -933,27 +1102,46 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
         if (r == LBM_OK && with_particles) r = launch_particles(s);
         return r;
     };
-    // without a per-update consumer (tracer particles, macro texture) a frame is one two-update sweep
+    // A frame is one two-update sweep whenever nothing mutates between its updates.  Tracer particles only READ the
+    // field (particle_update.wgsl:11,20): the sweep stores the texture of t+1 and of t+2, and the two particle passes
+    // run after it — same inputs, same order among themselves as fluid_simulator.rs:223-231.
     bool fused = false;
-    if (!with_particles && n_frames > 0 && (rc = fuse_eligible(s, &fused))) return rc;
-    if (fused) {
+    if (n_frames > 0 && (rc = fuse_eligible(s, &fused))) return rc;
+    if (!fused && (rc = ensure_mixed(s))) return rc;
+    if (fused && with_particles) {
+        if (!s->macro_mid) {
+            const size_t bytes = sizeof(__half) * 4 * (size_t)s->P.h * s->P.nx;
+            CU(cudaMalloc(&s->macro_mid, bytes));
+            CU(cudaMemsetAsync(s->macro_mid, 0, bytes, s->stream));
+        }
+        auto pframe = [&]() {
+            int r = launch_pair(s, 0, true);
+            if (r == LBM_OK) r = launch_particles(s, s->macro_mid);
+            if (r == LBM_OK) r = launch_particles(s);
+            return r;
+        };
         int left = n_frames;
-        const bool graphs = graphs_enabled(s) && n_frames >= kGraphSteps;
-        if (graphs && (rc = ensure_pair_graph(s))) return rc;
+        const bool graphs = graphs_enabled(s) && n_frames >= 4;
+        if (graphs && !s->graph_pframes[s->flip]) {
+            rc = capture_graph(s, &s->graph_pframes[s->flip], &s->graph_pframes_kernels[s->flip], [&]() {
+                int r = pframe();
+                return r == LBM_OK ? pframe() : r;
+            });
+            if (rc) return rc;
+        }
         CU(cudaEventRecord(s->ev0, s->stream));
         if (graphs) {
-            const int key = s->flip * 2 + s->swap;
-            for (; left >= kGraphSteps / 2; left -= kGraphSteps / 2) {
-                CU(cudaGraphLaunch(s->graph_pairs[key], s->stream));
-                s->launches += s->graph_pairs_kernels[key];
-                s->steps_since_reset += kGraphSteps;
-                s->macro_writes += kGraphSteps;
-                s->fused_sweeps += kGraphSteps / 2;
+            for (; left >= 2; left -= 2) {
+                CU(cudaGraphLaunch(s->graph_pframes[s->flip], s->stream));
+                s->launches += s->graph_pframes_kernels[s->flip];
+                s->steps_since_reset += 4;
+                s->macro_writes += 4;
+                s->fused_sweeps += 2;
                 s->prev_stale = true;
             }
         }
         for (; left > 0; left--)
-            if ((rc = launch_pair(s, 0))) return rc;
+            if ((rc = pframe())) return rc;
         CU(cudaEventRecord(s->ev1, s->stream));
         s->timed = true;
         return LBM_OK;
@@ -1060,6 +1248,7 @@ extern "C" int lbm_write_distributions(LbmSim *s, int32_t which, const float *sr
                              sizeof(float) * P.nx, P.h, cudaMemcpyHostToDevice, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     s->ring_check_needed = true; // restored solids may hold values a ring cell pulls (k_ring_check)
+    s->spare_keep_dirty = true;
     return LBM_OK;
 }
 

@@ -67,6 +67,7 @@ struct SlabParams {
                        // solid cell: bit (k-1) set = slot k is dead (its only reader is solid too)
     LatticeInfo *info; // (h+2) rows of nx: row 0 = halo y0-1, rows 1..h owned, row h+1 = halo
     __half *macro16;   // h*nx texels of 4 halfs, or nullptr
+    __half *macro16_mid; // two-update sweeps with tracer particles: the texture update 1 stores into (lbm_fused.cuh)
     float *macro32;    // 3 planes of h*nx f32 (u.x,u.y,rho), or nullptr
     Coef k;
 };

@@ -121,6 +121,26 @@ __global__ void __launch_bounds__(256) k_derive_halo(const __grid_constant__ Sla
     dn[x] = cd;
 }
 
+// ------------------------------------------------------------------ armed force cells in the info halo rows
+// The halo rows are copies of the neighbour slabs' edge rows.  The owners retire an armed inlet / force cell
+// (block_iter > 0) on the device — init.wgsl:51-59 at reset (material 1, block_iter 0, velocity 0: zero_v = 1), or
+// collide_stream.wgsl:55-62 when its countdown ends (material 1, block_iter 0, velocity kept) — and the copies must
+// follow, or the edge row blocks of a sweep would go on forcing a cell that is bulk by now.
+__global__ void __launch_bounds__(256) k_retire_halo(const __grid_constant__ SlabParams P, int zero_v) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= P.nx) return;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        LatticeInfo *ip = P.info + (k ? (size_t)(P.h + 1) * P.nx : (size_t)0) + x;
+        LatticeInfo in = *ip;
+        if ((in.material == 3 || in.material == 6) && in.block_iter > 0) {
+            in.material = 1; in.block_iter = 0;
+            if (zero_v) { in.vx = 0.0f; in.vy = 0.0f; }
+            *ip = in;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ stale values a ring cell would pull
 // A fluid cell on the outer ring never receives a bounce-back (boundary.wgsl:19), so when it pulls from a solid
 // neighbour it reads whatever that slot holds: 0 after init.wgsl, but a leftover value when the solid was painted

@@ -17,6 +17,9 @@ def pytest_configure(config):
     if not os.path.exists(so):
         subprocess.check_call([os.path.join(ROOT, "simuverse_b200", "csrc", "build.sh")],
                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    # test processes use the product's wire structs on both sides (tests/oracle.py picks them up when the package
+    # is already imported; on its own it loads wire.py without the package, see oracle._wire)
+    import simuverse_b200.wire  # noqa: F401
 
 
 @pytest.fixture(scope="session")

@@ -5,23 +5,35 @@ Test infrastructure: imported only from tests/, ``__graft_entry__.smoke()`` and 
 imports this module.
 """
 import ctypes as C
+import importlib.util
 import os
 import subprocess
+import sys
 
 import numpy as np
 
-from simuverse_b200.wire import (
-    LATTICE_INFO_DTYPE,
-    PARTICLE_DTYPE,
-    PIXEL_DTYPE,
-    FieldUniform,
-    LatticeInfo,
-    LbmUniform,
-    ParticleUniform,
-    ptr,
-)
-
 _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _wire():
+    """The wire structs (byte images of the reference's Pod structs).  Inside a process that already uses the
+    product package they are its ``simuverse_b200.wire`` classes (so structs can be handed back and forth);
+    otherwise — the CPU-only reference arm of bench.py — wire.py is loaded on its own, WITHOUT importing the
+    package, so that the product's shared library is never mapped into a process that only runs the oracle."""
+    m = sys.modules.get("simuverse_b200.wire")
+    if m is None:
+        spec = importlib.util.spec_from_file_location("_lbm_wire_standalone",
+                                                      os.path.join(_ROOT, "simuverse_b200", "wire.py"))
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    return m
+
+
+_w = _wire()
+LATTICE_INFO_DTYPE, PARTICLE_DTYPE, PIXEL_DTYPE = _w.LATTICE_INFO_DTYPE, _w.PARTICLE_DTYPE, _w.PIXEL_DTYPE
+FieldUniform, LatticeInfo, LbmUniform, ParticleUniform, ptr = (_w.FieldUniform, _w.LatticeInfo, _w.LbmUniform,
+                                                               _w.ParticleUniform, _w.ptr)
+
 _ORACLE_DIR = os.path.join(_ROOT, "oracle")
 _SO = os.path.join(_ORACLE_DIR, "liblbm_oracle.so")
 

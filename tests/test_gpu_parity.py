@@ -119,6 +119,7 @@ def test_macro_texture_every_step_matches_oracle(orc):
     sim.step(37)
     tex = node.read_macro_tex()
     np.testing.assert_array_equal(tex.view(np.uint16).reshape(-1), sim.macro_f16)
+    assert node.fused_sweep_count == 18, "the texture is written by the two-update sweeps"
     compare_state(node, sim, "37 steps with macro texture")
     # on-demand texture of a handle without the flag agrees too
     node2, _ = make_pair(orc, nx, ny, W.POISEUILLE)
@@ -364,6 +365,7 @@ def test_frame_loop_with_particles_matches_oracle(orc):
             sim.particle_update(field, pu, parts, canvas_o)
         orc.canvas_fade(field, pu, canvas_o)
     got = fs.fluid_compute_node.read_particles(n)
+    assert fs.fluid_compute_node.fused_sweep_count == 60, "every frame is one two-update sweep + two particle passes"
     assert got.tobytes() == parts.tobytes(), "particle trajectories differ"
     # canvas: pixels written by exactly the same set of particles; colliding writers race (reference too)
     cg = fs.fluid_compute_node.read_canvas().reshape(-1)
@@ -436,6 +438,8 @@ def test_cuda_matches_executed_reference_wgsl(path, flags):
         node.write_particle_uniform(pu)
         node.write_particles(g["particles_init"])
         fs.compute(steps // 2)
+        if flags == 0 and nx % 2 == 0:
+            assert node.fused_sweep_count == steps // 2, "frames with tracer particles run as sweeps"
         assert node.read_particles(num[0] * num[1]).tobytes() == g["particles"].tobytes(), "particle trajectories"
         cg = node.read_canvas().reshape(-1)
         assert ((cg["alpha"] != 0) == (g["canvas"]["alpha"] != 0)).all()
@@ -479,6 +483,8 @@ def test_cuda_matches_executed_reference_wgsl_default_config(flags):
     assert fs.lattice == (int(g["nx"]), int(g["ny"])) and fs.particles_num == (127, 80)
     fs.compute(int(g["frames"]))
     node = fs.fluid_compute_node
+    if flags == 0:
+        assert node.fused_sweep_count == int(g["frames"])
     assert node.swap_index == int(g["swap"])
     assert sha(node.read_distributions(node.swap_index)) == str(g["sha_cur"])
     if not flags & sb.FLAG_AA:

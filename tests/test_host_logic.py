@@ -159,6 +159,29 @@ def test_product_does_not_import_the_oracle():
                 assert "oracle" not in text.lower(), f"{f} mentions the oracle"
 
 
+def test_reference_arm_never_maps_the_product_library():
+    """`bench.py --impl reference` (and anything else that only needs the oracle) must not load liblbm_b200.so:
+    tests/oracle.py loads wire.py on its own when the product package has not been imported."""
+    import json
+    import subprocess
+    import sys
+
+    code = ("import sys, os; sys.path.insert(0, %r); import oracle; oracle.lib(); "
+            "assert not any(m.startswith('simuverse_b200') for m in sys.modules), 'package imported'; "
+            "maps = open('/proc/self/maps').read(); assert 'liblbm_b200' not in maps, 'product library mapped'; "
+            "assert 'liblbm_oracle' in maps; print('CLEAN')" % os.path.join(ROOT, "tests"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "CLEAN" in r.stdout, r.stdout + r.stderr
+    # the arm itself, on a small lattice: one JSON line whose `config` has the keys of the b200 arm's
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "3",
+                        "--lattice", "256", "128"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port"
+    assert set(line["config"]) == {"workload", "baseline_config", "lattice", "tau", "l2"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
 def test_cpp_host_mirror_compiles_and_runs(tmp_path):
     """include/d2q9_node.hpp (C++ mirror of D2Q9Node / FluidSimulator) builds against the library;
     on a CPU box it must report the missing GPU instead of computing anything."""
