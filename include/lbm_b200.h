@@ -21,6 +21,8 @@
  *   lbm_step_n                 the frame loop's alternation 0,1,0,1,...  fluid_simulator.rs:223-231
  *   lbm_compute_frames         FluidSimulator::compute, n times          fluid_simulator.rs:217-232
  *   lbm_read_macro             macro_tex (RGBA16F) contents              d2q9_node.rs:91-104
+ *   lbm_read_curl              _curl_cal_node + curl_tex contents        fluid_simulator.rs:36-71,
+ *                              = curl_update.wgsl:12-33
  *   lbm_particles_update       particle_update_node.compute_by_pass      fluid_simulator.rs:225,229
  *                              = particle_update.wgsl:55-88
  *   lbm_read_distributions /   (no reference equivalent: can_read_back=false,
@@ -154,6 +156,12 @@ int lbm_read_macro(LbmSim *sim, int32_t format, void *dst);
  * device-to-host copy of the RGBA16F texture on a separate stream and returns; later steps write a second
  * texture meanwhile.  dst (pinned host memory) is complete after lbm_sync. */
 int lbm_read_macro_async(LbmSim *sim, void *dst);
+/* The derived-field pass of the reference, lbm/curl_update.wgsl:12-33 (`_curl_cal_node`, fluid_simulator.rs:36-71;
+ * built there but never dispatched, :226,230): curl of the velocity in the newest macro texture, stored like the
+ * reference's `curl_tex` as RGBA16F texels (curl * 3.5 + 0.5, 0, 0, 0).  dst: rows*nx texels of 4 halfs.  The
+ * shader's right / bottom taps are clamped to lattice_size — one past the last texel — where wgpu reads zeros; that is
+ * reproduced.  Single-slab handles only (the reference is single-GPU and nothing consumes the texture). */
+int lbm_read_curl(LbmSim *sim, void *dst);
 /* Owned rows of the info buffer including device-side block_iter/material mutation
  * (collide_stream.wgsl:55-62). dst: rows*nx LatticeInfo. */
 int lbm_read_lattice_info(LbmSim *sim, LatticeInfo *dst);

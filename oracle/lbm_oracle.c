@@ -504,6 +504,32 @@ void orc_particle_update(const LbmUniform *u, const FieldUniform *field, const P
 }
 
 /* present.wgsl:19-22,43-49 */
+/* curl_update.wgsl:12-33 */
+static float orc_tex(const uint16_t *tex, int32_t nx, int32_t ny, int32_t x, int32_t y, int comp) {
+    if (x < 0 || x >= nx || y < 0 || y >= ny) return 0.0f; /* out-of-bounds textureLoad: zero (header comment) */
+    return orc_f16_to_f32(tex[4 * ((size_t)y * (size_t)nx + (size_t)x) + comp]);
+}
+
+void orc_curl_update(int32_t nx, int32_t ny, const uint16_t *macro_f16, uint16_t *curl_f16) {
+#pragma omp parallel for schedule(static)
+    for (int32_t y = 0; y < ny; y++)
+        for (int32_t x = 0; x < nx; x++) {
+            const int32_t rx = x + 1 < nx ? x + 1 : nx;   /* min(uv.x + 1, lattice_size.x)  (:21) */
+            const int32_t lx = x - 1 > 0 ? x - 1 : 0;     /* max(uv.x - 1, 0)               (:22) */
+            const int32_t ty = y - 1 > 0 ? y - 1 : 0;     /* max(uv.y - 1, 0)               (:23) */
+            const int32_t by = y + 1 < ny ? y + 1 : ny;   /* min(uv.y + 1, lattice_size.y)  (:24) */
+            /* min / max act on both components: y stays (y <= ny), x stays (x <= nx) */
+            float curl = orc_tex(macro_f16, nx, ny, rx, y, 1) - orc_tex(macro_f16, nx, ny, lx, y, 1);
+            curl = curl + orc_tex(macro_f16, nx, ny, x, ty, 0);
+            curl = curl - orc_tex(macro_f16, nx, ny, x, by, 0);
+            const size_t c = (size_t)y * (size_t)nx + (size_t)x;
+            curl_f16[4 * c + 0] = orc_f32_to_f16(curl * 3.5f + 0.5f); /* -ffp-contract=off: two roundings */
+            curl_f16[4 * c + 1] = orc_f32_to_f16(0.0f);
+            curl_f16[4 * c + 2] = orc_f32_to_f16(0.0f);
+            curl_f16[4 * c + 3] = orc_f32_to_f16(0.0f);
+        }
+}
+
 void orc_canvas_fade(const FieldUniform *field, const ParticleUniform *pu, Pixel *canvas) {
     const size_t n = (size_t)field->canvas_size[0] * (size_t)field->canvas_size[1];
     for (size_t i = 0; i < n; i++) {

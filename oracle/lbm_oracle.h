@@ -123,6 +123,13 @@ void orc_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas_h, int32_t
                                    int32_t num_y, float life_time, uint64_t seed,
                                    TrajectoryParticle *out);
 
+/* assets/wgsl/lbm/curl_update.wgsl:12-33 — the derived-field pass FluidSimulator builds but never dispatches
+ * (fluid_simulator.rs:226,230).  Per cell (no material test): curl = fb(right).y - fb(left).y + fb(top).x -
+ * fb(bottom).x on the RGBA16F macro texture, left/top clamped to 0 and right/bottom to lattice_size — ONE PAST the
+ * last texel (:21,24), where the load is out of bounds: zeros under wgpu (naga ReadZeroSkipWrite).  Stores
+ * (curl * 3.5 + 0.5, 0, 0, 0) as f16 texels. */
+void orc_curl_update(int32_t nx, int32_t ny, const uint16_t *macro_f16, uint16_t *curl_f16);
+
 /* f64 sum of one distribution buffer (all 9 planes) — the "total mass" diagnostic. */
 double orc_total_mass(int32_t nx, int32_t ny, const float *buf);
 

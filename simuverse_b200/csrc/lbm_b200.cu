@@ -58,6 +58,7 @@ struct LbmSim {
     double *d_mass = nullptr;
     float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
     __half *scratch16 = nullptr; // RGBA16F texels for the on-demand macro read
+    __half *curl16 = nullptr;    // RGBA16F texels of lbm_read_curl
     // second macro texture + copy stream for lbm_read_macro_async (pipelined field read-back)
     __half *macro_buf[2] = {nullptr, nullptr};
     int macro_cur = 0;
@@ -113,6 +114,7 @@ struct LbmSim {
     int stage_next = 0;
     size_t stage_cursor = 0;
     float *prev_spare = nullptr;           // single slab: persistent spare buffer of materialize_prev (allocated on first use)
+    float *prev_spare_alloc = nullptr;     // ... the allocation itself: after a pointer exchange the spare is a part of the arena
     bool spare_keep_dirty = true;          // the slots no update writes may differ between the spare and the real buffers
     // multi-slab only: a third distribution buffer in the arena (peer-visible), so that the buffer a sweep leaves two
     // updates behind can be recomputed by an ordinary, neighbour-synchronised update and swapped in
@@ -351,6 +353,12 @@ int fuse_geometry(LbmSim *s) {
         const long long resident = (long long)sms * std::max(per_sm, 1);
         H = (int)((long long)h * g.ctas_x / (6 * resident));
         H = std::max(h_min, std::min(H, h_max));
+        // A lattice too small to fill the GPU even once at h_min rows per block (the reference's own 600 x 375) is
+        // bound by the latency of a block's serial march, (H + 2) row iterations: the shortest blocks that still fit
+        // one wave (>= 2 rows: a neighbour slab reads two) finish soonest; their redundant update-1 rows cost nothing
+        // while SMs idle.
+        if ((long long)g.ctas_x * ((h + h_min - 1) / h_min) < resident && !getenv("LBM_FUSE_HMIN"))
+            H = (int)std::max<long long>(2, ((long long)h * g.ctas_x + resident - 1) / resident);
         // A warp streams 18 planes; with blocks that do not straddle 2 MB pages it needs one page per plane.  Measured
         // on slabs of 16384 x 2048 (64 KB rows, 32 rows per page): 32-row blocks 135 GLUPS per GPU, 31-row blocks 118.
         // Snap to a power-of-two fraction of the rows per page when the row pitch allows.
@@ -535,7 +543,8 @@ int materialize_prev(LbmSim *s) {
     const int old = s->swap ^ 1;
     const size_t bytes = sizeof(float) * 9 * P.plane;
     if (!s->prev_spare) {
-        CU(cudaMalloc(&s->prev_spare, bytes));
+        CU(cudaMalloc(&s->prev_spare_alloc, bytes));
+        s->prev_spare = s->prev_spare_alloc;
         CU(cudaMemsetAsync(s->prev_spare, 0, bytes, s->stream));
     }
     // Slots no update ever writes (a solid cell's live slot whose reader sits on the outer ring, boundary.wgsl:19)
@@ -629,7 +638,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->macro_buf[0] ? s->macro_buf[0] : s->P.macro16);
     cudaFree(s->macro_buf[1]);
     cudaFree(s->macro_mid);
-    cudaFree(s->prev_spare);
+    cudaFree(s->prev_spare_alloc);
     for (auto p : s->stage) if (p) cudaFreeHost(p);
     for (auto e : s->stage_ev) if (e) cudaEventDestroy(e);
     if (s->ev_ready) cudaEventDestroy(s->ev_ready);
@@ -637,6 +646,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     cudaFree(s->scratch32);
     cudaFree(s->scratch16);
+    cudaFree(s->curl16);
     cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
     cudaFree(s->d_fuse_flags);
@@ -649,6 +659,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->stream) cudaStreamDestroy(s->stream);
+    cudaGetLastError(); // nothing from the teardown may surface as another handle's launch failure
     delete s;
 }
 
@@ -1146,6 +1157,28 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
         s->timed = true;
         return LBM_OK;
     }
+    if (fused) { // no tracer particles: a frame is one launch
+        int left = n_frames;
+        const bool graphs = graphs_enabled(s) && n_frames >= kGraphSteps;
+        if (graphs && (rc = ensure_pair_graph(s))) return rc;
+        CU(cudaEventRecord(s->ev0, s->stream));
+        if (graphs) {
+            const int key = s->flip * 2 + s->swap;
+            for (; left >= kGraphSteps / 2; left -= kGraphSteps / 2) {
+                CU(cudaGraphLaunch(s->graph_pairs[key], s->stream));
+                s->launches += s->graph_pairs_kernels[key];
+                s->steps_since_reset += kGraphSteps;
+                s->macro_writes += kGraphSteps;
+                s->fused_sweeps += kGraphSteps / 2;
+                s->prev_stale = true;
+            }
+        }
+        for (; left > 0; left--)
+            if ((rc = launch_pair(s, 0))) return rc;
+        CU(cudaEventRecord(s->ev1, s->stream));
+        s->timed = true;
+        return LBM_OK;
+    }
     const bool use_graph = graphs_enabled(s) && n_frames >= 4;
     if (use_graph && !s->graph_frame) {
         rc = capture_graph(s, &s->graph_frame, &s->graph_frame_kernels, frame);
@@ -1298,6 +1331,48 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
         CU(cudaMemcpyAsync(dst, Q.macro32, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, s->stream));
     else
         CU(cudaMemcpyAsync(dst, Q.macro16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// curl_update.wgsl over the newest macro texture (the step's own texture, or the on-demand one).
+extern "C" int lbm_read_curl(LbmSim *s, void *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (s->d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "lbm_read_curl is single-slab only");
+    CU(cudaSetDevice(s->device));
+    const SlabParams &P = s->P;
+    const size_t n = (size_t)P.h * P.nx;
+    const __half *tex = nullptr;
+    if (P.macro16) {
+        tex = (s->macro_writes == s->macro_writes_at_flip) ? s->macro_buf[s->macro_cur ^ 1] : P.macro16;
+    } else {
+        // no per-step texture: produce it like lbm_read_macro(LBM_MACRO_RGBA16F) does
+        if (s->aa && s->steps_since_reset != 0)
+            return fail(s, LBM_ERR_UNSUPPORTED, "in-place (AA) handle: create it with LBM_FLAG_MACRO_EVERY_STEP to read derived fields");
+        int rc = ready_to_step(s);
+        if (rc) return rc;
+        if ((rc = materialize_prev(s))) return rc;
+        if ((rc = ensure_scratch16(s))) return rc;
+        SlabParams Q = P;
+        Q.macro16 = s->scratch16;
+        Q.macro32 = nullptr;
+        if (s->steps_since_reset == 0) {
+            k_macro_after_init<<<148 * 8, 256, 0, s->stream>>>(Q);
+            rc = check_launch(s, "k_macro_after_init");
+        } else {
+            dim3 block(64, 4);
+            k_step_generic<1><<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(Q, s->swap ^ 1, 0, P.h);
+            rc = check_launch(s, "k_step_generic<macro>");
+        }
+        if (rc) return rc;
+        tex = s->scratch16;
+    }
+    if (!s->curl16) CU(cudaMalloc(&s->curl16, sizeof(__half) * 4 * n));
+    dim3 block(64, 4);
+    k_curl<<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(tex, P.nx, P.h, s->curl16);
+    int rc = check_launch(s, "k_curl");
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, s->curl16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return LBM_OK;
 }

@@ -81,6 +81,29 @@ __global__ void __launch_bounds__(256) k_particle_update(const __half *__restric
     particles[p_index] = p;
 }
 
+// curl_update.wgsl:12-33 — derived field of the macro texture (the reference's `_curl_cal_node`).  One thread per
+// texel; taps left / top are clamped to 0, right / bottom to lattice_size, i.e. ONE PAST the last texel (:21,24),
+// where textureLoad is out of bounds and wgpu returns zeros (naga ReadZeroSkipWrite).  f16 texels convert to f32
+// exactly; the three additions and `curl * 3.5 + 0.5` are single IEEE operations in source order.
+__global__ void __launch_bounds__(256) k_curl(const __half *__restrict__ macro16, int nx, int ny, __half *__restrict__ curl16) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= nx || y >= ny) return;
+    auto tap = [&](int u, int v, int comp) -> float {
+        if (u < 0 || u >= nx || v < 0 || v >= ny) return 0.0f;
+        return __half2float(macro16[4 * ((size_t)v * nx + u) + comp]);
+    };
+    const int rx = min(x + 1, nx), lx = max(x - 1, 0), ty = max(y - 1, 0), by = min(y + 1, ny);
+    float curl = fsub(tap(rx, y, 1), tap(lx, y, 1));
+    curl = fadd(curl, tap(x, ty, 0));
+    curl = fsub(curl, tap(x, by, 0));
+    const __half2 a = __floats2half2_rn(fadd(fmul(curl, 3.5f), 0.5f), 0.0f);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t *>(&a);
+    t.y = 0u;
+    reinterpret_cast<uint2 *>(curl16)[(size_t)y * nx + x] = t;
+}
+
 // present.wgsl:19-22,43-49 — the in-place fade of the canvas that the present pass performs
 __global__ void __launch_bounds__(256) k_canvas_fade(Pixel *canvas, size_t n, float fade_out_factor) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

@@ -245,6 +245,13 @@ class D2Q9Node:
         assert out.dtype == np.float16 and out.size == self.rows * self.lattice[0] * 4 and out.flags["C_CONTIGUOUS"]
         check(lib.lbm_read_macro_async(self._h, ptr(out)), self._h)
 
+    def read_curl_tex(self):
+        """``curl_tex`` of the reference's ``_curl_cal_node`` (fluid_simulator.rs:36-71, curl_update.wgsl:12-33) for
+        the newest macro field: (rows, nx, 4) float16 texels (curl * 3.5 + 0.5, 0, 0, 0)."""
+        out = np.empty((self.rows, self.lattice[0], 4), np.float16)
+        check(lib.lbm_read_curl(self._h, ptr(out)), self._h)
+        return out
+
     def read_lattice_info(self):
         out = np.empty(self.rows * self.lattice[0], dtype=LATTICE_INFO_DTYPE)
         check(lib.lbm_read_lattice_info(self._h, ptr(out)), self._h)

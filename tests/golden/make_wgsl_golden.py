@@ -50,6 +50,13 @@ def case_channel():
     return dict(nx=nx, ny=ny, fluid_ty=0, info=channel(nx, ny), steps=40, post=[])
 
 
+def case_channel100():
+    """north_star's bar is stated "after 100 steps": the channel with obstacles (inlet, outlet, ghost columns, walls,
+    a disc and a bar) for exactly 100 updates of the reference's WGSL."""
+    nx, ny = 64, 48
+    return dict(nx=nx, ny=ny, fluid_ty=0, info=channel(nx, ny), steps=100, post=[])
+
+
 def case_cavity():
     nx, ny = 40, 32
     return dict(nx=nx, ny=ny, fluid_ty=1, info=init_lattice_material(nx, ny, W.LID_DRIVEN_CAVITY), steps=40, post=[])
@@ -94,7 +101,7 @@ def case_midrun():
 
 CASES = {"wgsl_midrun_48x36_s44": case_midrun, "wgsl_channel_72x48_s40": case_channel, "wgsl_cavity_40x32_s40": case_cavity,
          "wgsl_force_36x30_s100": case_force, "wgsl_periodic_22x14_s30": case_periodic,
-         "wgsl_particles_60x40_f20": case_particles}
+         "wgsl_particles_60x40_f20": case_particles, "wgsl_channel100_64x48_s100": case_channel100}
 
 
 def main():

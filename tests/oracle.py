@@ -89,6 +89,7 @@ def lib():
         L.orc_field_uniform_new.argtypes = [i32, i32, u32, i32, i32, C.POINTER(FieldUniform)]
         L.orc_particle_grid.argtypes = [u32, u32, i32, C.POINTER(i32), C.POINTER(i32)]
         L.orc_init_trajectory_particles.argtypes = [u32, u32, i32, i32, f32, u64, vp]
+        L.orc_curl_update.argtypes = [i32, i32, vp, vp]
         L.orc_total_mass.restype = C.c_double
         L.orc_total_mass.argtypes = [i32, i32, vp]
         _lib = L
@@ -172,6 +173,15 @@ class OracleSim:
     def particle_update(self, field, pu, particles, canvas):
         lib().orc_particle_update(C.byref(self.u), C.byref(field), C.byref(pu), ptr(particles),
                                   ptr(canvas) if canvas is not None else None, ptr(self.macro_f16))
+
+
+def curl_update(nx, ny, macro_f16):
+    """curl_update.wgsl over an RGBA16F macro texture given as uint16 bits; returns (ny, nx, 4) uint16."""
+    macro_f16 = np.ascontiguousarray(macro_f16, np.uint16).reshape(-1)
+    assert macro_f16.size == 4 * nx * ny
+    out = np.zeros(4 * nx * ny, np.uint16)
+    lib().orc_curl_update(nx, ny, ptr(macro_f16), ptr(out))
+    return out.reshape(ny, nx, 4)
 
 
 def canvas_fade(field, pu, canvas):

@@ -45,11 +45,12 @@ def test_launch_regimes_match_oracle(orc, period, regime):
     # small-lattice rule (always inline) does not apply
     info = striped_mask(orc, nx, ny, period)
     node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.CUSTOM), lattice=(nx, ny), lattice_info=info, flags=sb.FLAG_NO_FUSE)
+    node.step_n(1)  # the first single update after a mask change also rebuilds the mixed-warp list (k_scan_mixed)
     before = node.launch_count
     node.step_n(3)
     per_step = (node.launch_count - before) / 3
     assert per_step == (1 if regime == "rare" else 2), f"{regime}: {per_step} launches per update"
-    node.step_n(57)
+    node.step_n(56)
     sim = oracle_for(orc, nx, ny, info)
     sim.step(60)
     for which in (0, 1):
@@ -230,29 +231,6 @@ def test_call_order_errors_are_reported_not_fatal():
     lib.lbm_generate_lattice_info(h, W.POISEUILLE, 0, 0.0)
     assert lib.lbm_step_n(h, 1) == _capi.ERR_STATE and b"lbm_ipc_attach" in lib.lbm_last_error(h)
     lib.lbm_destroy(h)
-
-
-def test_full_size_properties_8192_porous_and_16384():
-    """BASELINE's largest single-GPU shapes through size-independent properties: the production kernels
-    agree with the one-thread-per-cell kernel bit for bit, every value respects the per-direction clamp,
-    and the f64 mass of the two runs is identical."""
-    for nx, ny, preset, steps in [(8192, 8192, sb.PRESET_POROUS, 6), (16384, 16384, W.POISEUILLE, 4)]:
-        kw = dict(lattice=(nx, ny), device_preset=preset)
-        a = sb.D2Q9Node((nx * 2, ny * 2), setting(W.POISEUILLE), **kw)
-        a.step_n(steps)
-        mass_a = a.total_mass()
-        rows = slice(ny // 2 - 2, ny // 2 + 2)
-        cur_a = a.read_distributions(a.swap_index)[:, rows].copy()
-        a.close()
-        b = sb.D2Q9Node((nx * 2, ny * 2), setting(W.POISEUILLE), flags=sb.FLAG_KERNEL_GENERIC, **kw)
-        b.step_n(steps)
-        assert abs(b.total_mass() - mass_a) <= 1e-12 * mass_a  # f64 atomics: summation order is not fixed
-        cur_b = b.read_distributions(b.swap_index)[:, rows].copy()
-        b.close()
-        assert_bits_equal(cur_a, cur_b, f"{nx}x{ny} production vs generic kernel")
-        mx = [0.6] + [0.2222] * 4 + [0.1111] * 4
-        for i in range(9):
-            assert cur_a[i].min() >= 0.0 and cur_a[i].max() <= np.float32(mx[i])
 
 
 def test_lost_neighbour_times_out_instead_of_hanging(orc):

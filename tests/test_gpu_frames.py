@@ -262,3 +262,28 @@ def test_slabs_resume_sweeps_after_interior_edits_and_armed_cells_on_cuts(orc, n
     check("solid next to the ring", live)
     assert [n.fused_sweep_count for n in grp.nodes] == sweeps
     grp.close()
+
+
+def test_curl_pass_matches_executed_wgsl_and_oracle(orc):
+    """lbm_read_curl (curl_update.wgsl:12-33, the reference's never-dispatched `_curl_cal_node`)."""
+    from helpers import WGSL_CURL
+
+    g = np.load(WGSL_CURL)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    c100 = np.load(WGSL_CURL.replace("wgsl_curl_64x48", "wgsl_channel100_64x48_s100"))
+    # the channel case of the golden, 100 updates: texture handle (sweeps) and on-demand handle
+    for flags in (sb.FLAG_MACRO_EVERY_STEP, 0):
+        a = node_for(nx, ny, W.CUSTOM, c100["info"], flags=flags)
+        a.step_n(100)
+        np.testing.assert_array_equal(a.read_macro_tex().view(np.uint16), g["macro_f16"].reshape(ny, nx, 4))
+        np.testing.assert_array_equal(a.read_curl_tex().view(np.uint16), g["curl_f16"], err_msg=f"flags {flags}")
+        a.close()
+    # a larger lattice against the oracle, odd sizes included
+    for nx, ny, preset in [(600, 375, W.POISEUILLE), (131, 77, W.LID_DRIVEN_CAVITY)]:
+        info = orc.init_lattice_material(nx, ny, preset)
+        a = node_for(nx, ny, preset, info, flags=sb.FLAG_MACRO_EVERY_STEP)
+        sim = oracle_for(orc, nx, ny, preset, info)
+        a.step_n(60)
+        sim.step(60)
+        np.testing.assert_array_equal(a.read_curl_tex().view(np.uint16), orc.curl_update(nx, ny, sim.macro_f16))
+        a.close()

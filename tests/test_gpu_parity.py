@@ -262,34 +262,7 @@ def test_mass_trajectory_10k_steps(orc):
     node.close()
 
 
-def test_full_size_4096_against_oracle_and_properties(orc):
-    """Config 2 at BASELINE's full size: device-generated mask CRC (bit-exact indexing), 6 steps
-    compared with the oracle cell by cell, then size-independent properties."""
-    nx = ny = 4096
-    node = sb.D2Q9Node((nx * 2, ny * 2), setting(W.POISEUILLE), lattice=(nx, ny), device_preset=W.POISEUILLE)
-    info = node.read_lattice_info()
-    assert zlib.crc32(info["material"].astype("<i4").tobytes()) == 0x63A17811
-    sim = orc.OracleSim(nx, ny, info, orc.uniform_new(tau_default(), 0, nx * ny), threads=orc.lib().orc_get_max_threads())
-    assert abs(node.total_mass() - sim.total_mass()) / sim.total_mass() < 1e-9
-    node.step_n(6)
-    sim.step(6)
-    for which in (0, 1):
-        assert_bits_equal(node.read_distributions(which), sim.distributions(which), f"4096^2 buf{which}")
-    del sim
-    # properties: bounds of the per-direction clamp, solids never written, generic kernel agrees
-    cur = node.read_distributions(node.swap_index)
-    mx = [0.6] + [0.2222] * 4 + [0.1111] * 4
-    for i in range(9):
-        assert cur[i].min() >= 0.0 and cur[i].max() <= np.float32(mx[i])
-    ring_solid = np.zeros((ny, nx), bool)
-    ring_solid[0, :] = ring_solid[-1, :] = True
-    assert (cur[0][ring_solid] == 0).all()
-    gen = sb.D2Q9Node((nx * 2, ny * 2), setting(W.POISEUILLE), lattice=(nx, ny), device_preset=W.POISEUILLE,
-                      flags=sb.FLAG_KERNEL_GENERIC)
-    gen.step_n(6)
-    assert_bits_equal(gen.read_distributions(gen.swap_index), cur, "generic vs vectorised kernel at 4096^2")
-    node.close()
-    gen.close()
+# (BASELINE's full sizes against the oracle: tests/test_gpu_fullsize.py)
 
 
 # ------------------------------------------------------------------ y-slab decomposition on one GPU

@@ -323,3 +323,22 @@ def test_oracle_matches_executed_reference_wgsl_default_config(orc):
     rows = list(g["rows"])
     assert_bits_equal(s.distributions(s.swap)[:, rows, :], g["cur_rows"], "rows of the current buffer")
     assert abs(s.total_mass() - float(g["total_mass"])) < 1e-6
+
+
+def test_curl_pass_matches_executed_reference_wgsl(orc):
+    """oracle.curl_update against the texture produced by executing lbm/curl_update.wgsl (tests/golden/
+    make_wgsl_golden_curl.py), plus the clamp quirk: the right / bottom taps of the last column / row are out of bounds
+    and read zeros."""
+    from helpers import WGSL_CURL
+
+    g = np.load(WGSL_CURL)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    got = orc.curl_update(nx, ny, g["macro_f16"])
+    np.testing.assert_array_equal(got, g["curl_f16"])
+    assert (got[..., 1:] == 0).all()
+    # a field with u.y = 1 everywhere: interior curl = 0 -> 0.5; last column: right tap reads 0 -> curl = -1 -> -3.0;
+    # column 0: left tap clamps onto itself -> 0 -> 0.5
+    tex = np.zeros((5, 7, 4), np.float16)
+    tex[..., 1] = 1.0
+    c = orc.curl_update(7, 5, tex.view(np.uint16)).view(np.float16)[..., 0]
+    assert (c[:, :6] == 0.5).all() and (c[:, 6] == -3.0).all()

@@ -80,6 +80,22 @@ class WgslLbm:
             self.dispatch("boundary", rd, wr)
             self.swap ^= 1
 
+    # ---- derived field (curl_update.wgsl; never dispatched by the reference: fluid_simulator.rs:226,230)
+    def curl_update(self):
+        """Dispatches lbm/curl_update.wgsl over the current macro texture; returns the (ny, nx, 4) f16 curl texture."""
+        if "curl_update" not in self.mods:
+            self.mods["curl_update"] = _load("lbm/curl_update.wgsl")
+            self._bind_common(self.mods["curl_update"])
+        ns = self.mods["curl_update"]
+        curl = np.zeros((self.ny, self.nx, 4), np.float16)
+        ns["fb"] = rt.Texture16F(self.macro)
+        ns["curl_info"] = rt.Texture16F(curl)
+        main = ns["cs_main"]
+        for gy in range(-(-self.ny // 4) * 4):
+            for gx in range(-(-self.nx // 64) * 64):
+                main(rt.Vec([gx, gy, 0]))
+        return curl
+
     # ---- particles (particle_update.wgsl)
     def bind_particles(self, pu, particles, canvas):
         ns = self.mods["particle_update"]

@@ -209,4 +209,10 @@ def textureStore(tex, uv, value):
 
 def textureLoad(tex, uv, level):
     x, y = int(uv.v[0]), int(uv.v[1])
+    ny, nx = tex.arr.shape[:2]
+    if not (0 <= x < nx and 0 <= y < ny):
+        # WGSL leaves an out-of-bounds textureLoad to the implementation (zero, (0,0,0,1) or some in-bounds texel);
+        # wgpu compiles shaders with naga's BoundsCheckPolicy::ReadZeroSkipWrite for image loads, i.e. zeros.  Only
+        # lbm/curl_update.wgsl gets here (its `min(.., lattice_size)` clamp is one past the last texel).
+        return Vec([F(0.0)] * 4)
     return Vec([F(c) for c in tex.arr[y, x, :].astype(np.float32)])

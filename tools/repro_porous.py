@@ -1,0 +1,10 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import simuverse_b200 as sb
+from simuverse_b200 import wire as W
+nx, ny = int(sys.argv[1]), int(sys.argv[2])
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+a = sb.D2Q9Node((nx * 2, ny * 2), sb.SettingObj(animation_type=W.POISEUILLE), lattice=(nx, ny), device_preset=sb.PRESET_POROUS, flags=flags)
+a.step_n(6)
+print("mass", a.total_mass(), "sweeps", a.fused_sweep_count)
+a.close()
