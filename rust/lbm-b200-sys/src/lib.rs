@@ -130,6 +130,7 @@ unsafe extern "C" {
     pub fn lbm_write_distributions(sim: *mut LbmSim, which: i32, src: *const f32) -> c_int;
     pub fn lbm_read_macro(sim: *mut LbmSim, format: i32, dst: *mut c_void) -> c_int;
     pub fn lbm_read_macro_async(sim: *mut LbmSim, dst: *mut c_void) -> c_int;
+    pub fn lbm_read_curl(sim: *mut LbmSim, dst: *mut c_void) -> c_int;
     pub fn lbm_read_lattice_info(sim: *mut LbmSim, dst: *mut LatticeInfo) -> c_int;
     pub fn lbm_total_mass(sim: *mut LbmSim, which: i32, out: *mut f64) -> c_int;
 
@@ -148,6 +149,7 @@ unsafe extern "C" {
     pub fn lbm_sweep_blocks(h: i32, rows_per_block: i32, out: *mut i32, cap: i32, n_edge: *mut i32) -> i32;
     pub fn lbm_launch_count(sim: *const LbmSim) -> u64;
     pub fn lbm_fused_sweep_count(sim: *const LbmSim) -> u64;
+    pub fn lbm_sweep_uses_masked_path(sim: *const LbmSim) -> c_int;
     pub fn lbm_last_step_n_ms(sim: *mut LbmSim, ms: *mut f32) -> c_int;
     pub fn lbm_stream(sim: *mut LbmSim) -> *mut c_void;
 }

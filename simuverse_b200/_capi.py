@@ -90,6 +90,7 @@ PROTOTYPES = {
     "lbm_refresh_previous": (C.c_int, [_H]),
     "lbm_launch_count": (_u64, [_H]),
     "lbm_fused_sweep_count": (_u64, [_H]),
+    "lbm_sweep_uses_masked_path": (C.c_int, [_H]),
     "lbm_last_step_n_ms": (C.c_int, [_H, C.POINTER(_f32)]),
     "lbm_stream": (_vp, [_H]),
     # host-side mirrors

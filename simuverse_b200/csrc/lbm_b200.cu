@@ -102,6 +102,8 @@ struct LbmSim {
     bool fuse_blocked = false;             // a ring cell would pull a stale value out of a solid (see k_ring_check)
     bool ring_check_needed = false;
     bool mask_written_since_reset = false;
+    bool use_masked = false;               // sweep kernel instance with the inline masked path (choose_masked)
+    unsigned long long *d_non_plain = nullptr;
     bool mixed_dirty = false;              // the mask changed: the mixed-warp list is rebuilt before the next single update
     bool halo_retire_pending = false;      // multi-slab: armed force cells in the info halo rows retire when the countdown ends
     // pinned staging ring of lbm_write_lattice_info: the caller's bytes are copied here and travel asynchronously, so
@@ -171,15 +173,34 @@ void invalidate_step_graphs(LbmSim *s);
 // back here.  The mixed-warp list of the single-update kernels is rebuilt lazily (ensure_mixed), and only the graphs
 // that contain those kernels are dropped — a two-update sweep does not depend on the mask geometry.
 // want_armed: also collect the largest armed block_iter of the rows into d_fuse_flags[0] (read by the caller).
+// A derive over the whole slab (reset, preset generation, an upload of most of the mask) also counts the non-plain
+// cells and reads the count back (those calls are heavyweight anyway): above kMaskedShare of the slab the sweeps use the
+// kernel instance with the inline masked path (see k_frame2).
+constexpr double kMaskedShare = 0.02;
+
 int derive_rows(LbmSim *s, int l0, int l1, bool want_armed = false) {
     l0 = std::max(l0, 0);
     l1 = std::min(l1, s->P.h);
     if (l0 >= l1) return LBM_OK;
     dim3 block(64, 4);
+    const bool whole = l0 == 0 && l1 == s->P.h;
     if (want_armed) CU(cudaMemsetAsync(s->d_fuse_flags, 0, sizeof(unsigned int), s->stream));
-    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, want_armed ? s->d_fuse_flags : nullptr);
+    if (whole) CU(cudaMemsetAsync(s->d_non_plain, 0, sizeof(unsigned long long), s->stream));
+    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, want_armed ? s->d_fuse_flags : nullptr,
+                                                                        whole ? s->d_non_plain : nullptr);
     int rc = check_launch(s, "k_derive");
     if (rc) return rc;
+    if (whole) {
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, s->d_non_plain, sizeof(n), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        const bool masked = getenv("LBM_FUSE_MASKED") ? atoi(getenv("LBM_FUSE_MASKED")) != 0
+                                                      : (double)n > kMaskedShare * (double)s->P.h * (double)s->P.nx;
+        if (masked != s->use_masked) {
+            s->use_masked = masked;
+            invalidate_graphs(s);
+        }
+    }
     if (s->cls_halo) {
         k_derive_halo<<<(s->P.pitch + 255) / 256, 256, 0, s->stream>>>(s->P, s->cls_halo, s->cls_halo + s->P.pitch);
         if ((rc = check_launch(s, "k_derive_halo"))) return rc;
@@ -343,8 +364,8 @@ int fuse_geometry(LbmSim *s) {
     if (H <= 0) {
         int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
-        if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true, 0>, kFuseThreads, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false, 0>, kFuseThreads, 0);
+        if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true, 0, false>, kFuseThreads, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false, 0, false>, kFuseThreads, 0);
         // Uniform height giving at least ~6 waves of CTAs (measured on B200: with fewer the sweep ends in a long
         // tail; 4096^2 is best at 16 rows, 16384^2 at 32), between 8 and 32 rows.
         int h_min = 8, h_max = 32;
@@ -464,12 +485,18 @@ int fuse_eligible(LbmSim *s, bool *ok) {
     return LBM_OK;
 }
 
+template <bool SYMW, bool SLABS, bool MASKED>
+void launch_frame2m(const LbmSim *s, unsigned int grid, int first, int macro) {
+    const FuseGeom &g = s->fuse;
+    if (macro == 2) k_frame2<SYMW, SLABS, 2, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    else if (macro == 1) k_frame2<SYMW, SLABS, 1, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    else k_frame2<SYMW, SLABS, 0, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+}
+
 template <bool SYMW, bool SLABS>
 void launch_frame2(const LbmSim *s, unsigned int grid, int first, int macro) {
-    const FuseGeom &g = s->fuse;
-    if (macro == 2) k_frame2<SYMW, SLABS, 2><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-    else if (macro == 1) k_frame2<SYMW, SLABS, 1><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-    else k_frame2<SYMW, SLABS, 0><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    if (s->use_masked) launch_frame2m<SYMW, SLABS, true>(s, grid, first, macro);
+    else launch_frame2m<SYMW, SLABS, false>(s, grid, first, macro);
 }
 
 // Two updates starting from buffer `first`: ONE launch, then the pointer exchange.  With a macro texture the sweep
@@ -650,6 +677,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
     cudaFree(s->d_fuse_flags);
+    cudaFree(s->d_non_plain);
     cudaFree(s->d_fuse_rows);
     cudaFree(s->cls_halo);
     cudaFree(s->mixed.list);
@@ -723,6 +751,7 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     CU(cudaMalloc(&P.nbr, cells));
     CU(cudaMemsetAsync(P.cls, CLS_SOLID, cells, s->stream));
     CU(cudaMemsetAsync(P.nbr, 0, cells, s->stream));
+    CU(cudaMalloc(&s->d_non_plain, sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_fuse_flags, 2 * sizeof(unsigned int)));
     CU(cudaMemsetAsync(s->d_fuse_flags, 0, 2 * sizeof(unsigned int), s->stream));
     if (d.world > 1) {
@@ -1583,6 +1612,7 @@ extern "C" int lbm_ipc_attach(LbmSim *s, const LbmIpcBlob *up, const LbmIpcBlob 
 
 extern "C" uint64_t lbm_launch_count(const LbmSim *s) { return s ? s->launches : 0; }
 extern "C" uint64_t lbm_fused_sweep_count(const LbmSim *s) { return s ? s->fused_sweeps : 0; }
+extern "C" int lbm_sweep_uses_masked_path(const LbmSim *s) { return s && s->use_masked ? 1 : 0; }
 
 extern "C" int lbm_last_step_n_ms(LbmSim *s, float *ms) {
     if (!s || !ms) return fail(s, LBM_ERR_INVALID_ARG, "null argument");

@@ -282,6 +282,11 @@ class D2Q9Node:
         """Launches that advanced the lattice by two updates at once (csrc/lbm_fused.cuh)."""
         return int(lib.lbm_fused_sweep_count(self._h))
 
+    @property
+    def sweep_uses_masked_path(self):
+        """Whether sweeps run the kernel instance with the inline masked path (lattices with many solid cells)."""
+        return bool(lib.lbm_sweep_uses_masked_path(self._h))
+
     # ------------------------------------------------------------------ particles
     def write_particle_uniform(self, pu):
         check(lib.lbm_write_particle_uniform(self._h, C.byref(pu)), self._h)
