@@ -45,12 +45,22 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(config, overridden, fused=False):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+def measured_traffic(config, overridden, fused=False, world=1):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu captures (profiles/traffic.json).  Multi-slab
+    runs of config 3: the capture of one 16384x2048 slab at 8 slabs; for 2 and 4 slabs the one-slab figure / N (the slab
+    instance moves the same bytes per site, profiles/r02_k_frame2_slab_ncu_full.md)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = str(config) + ("_fused" if fused else "")
-        if not overridden and key in t:
+        if overridden:
+            return None, None
+        if world > 1:
+            if config != 3 or not fused:
+                return None, None
+            if world == 8:
+                return t["3_fused_slab8"]["bytes_per_launch"], t["3_fused_slab8"]["source"]
+            return t[key]["bytes_per_launch"] // world, t[key]["source"] + f" / {world} slabs"
+        if key in t:
             return t[key]["bytes_per_launch"], t[key]["source"]
     except Exception:
         pass
@@ -132,6 +142,34 @@ class ClockSampler:
         reasons = [name for b, name in self.REASONS.items() if bits & b]
         return {"sm_mhz": statistics.median(s[1] for s in win), "sm_max_mhz": self.max_mhz, "reasons": reasons,
                 "samples": len(win)}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pins this process (and, by first touch, the pinned host buffers it allocates afterwards) to the CPUs of the NUMA
+    node GPU `index` hangs off: with N ranks reading their fields back at once, buffers that all land on one socket
+    share that socket's memory and PCIe root.  Returns a short description for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:      # 00000000:1B:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip()
+        cpus = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return f"numa node {node}, {len(ids)} cpus"
+    except Exception as e:  # not fatal: the run is only slower
+        return f"unbound ({type(e).__name__})"
 
 
 def shared_config(name, config, nx, ny, world):
@@ -292,6 +330,7 @@ def main():
     if sb.lib.lbm_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: simuverse_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -357,6 +396,7 @@ def main():
         wl.advance(node, args.warmup + (args.warmup % 2))
         barrier(node)
         launches0, sweeps0 = node.launch_count, node.fused_sweep_count
+        wait0 = node.edge_wait_stats() if world > 1 else (0, 0)
         t0 = time.perf_counter()
         wl.advance(node, steps)          # CUDA events recorded around the launches on the library's stream
         ms = node.last_step_n_ms()       # synchronises on the end event
@@ -364,6 +404,11 @@ def main():
         t1 = time.perf_counter()
         r = {"steps": steps, "launches": node.launch_count - launches0, "sweeps": node.fused_sweep_count - sweeps0,
              "clocks": sampler.stop(t0, t1), "ms": reduce_max(ms), "host_wall_ms": (t1 - t0) * 1e3}
+        if world > 1:
+            wait_ns, waits = node.edge_wait_stats()
+            r["edge_wait"] = {"cta_ms_summed_max_over_ranks": reduce_max((wait_ns - wait0[0]) * 1e-6),
+                              "waits": waits - wait0[1],
+                              "mean_us_per_wait": ((wait_ns - wait0[0]) / max(waits - wait0[1], 1)) * 1e-3}
         r["value"] = wl.sites * steps / (r["ms"] * 1e-3) / 1e6
         if with_details:
             r["mass"] = slab.total_mass() if slab is not None else node.total_mass()
@@ -393,7 +438,7 @@ def main():
         per_launch_s = r["ms"] * 1e-3 / max(lattice_launches, 1)
         alg = BYTES_PER_SITE * (wl.sites / world) * updates_per_launch
         achieved = alg / per_launch_s / 1e9
-        traffic, traffic_src = measured_traffic(wl.config, overridden, fused)
+        traffic, traffic_src = measured_traffic(wl.config, overridden, fused, world)
         return fused, updates_per_launch, {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -466,7 +511,7 @@ def main():
                "d2h_bytes_per_step": d2h * world // per_call,
                "steps": args.e2e_steps * per_call,
                "two_update_sweeps": node2.fused_sweep_count - sweeps0,
-               "d2h_GBps_per_rank": d2h * args.e2e_steps / dt / 1e9,
+               "d2h_GBps_per_rank": d2h * args.e2e_steps / dt / 1e9, "host_binding": numa,
                "what": ("per host call, per rank: lbm_write_lattice_info(56-row LatticeInfo patch from pinned host memory) + "
                         + ("lbm_compute_frames(1) [= FluidSimulator::compute: 2 updates + 2 particle updates] + "
                            "lbm_particles_read + " if kind == "frames" else
@@ -515,7 +560,7 @@ def main():
                      "macro_on": ({"value": m2["value"], "unit": "MLUPS", "two_update_sweeps": m2["sweeps"]} if m2 else None)}
 
     if rank == 0:
-        fused, updates_per_launch, roof = roofline_of(wl, main_r, overridden or world > 1)
+        fused, updates_per_launch, roof = roofline_of(wl, main_r, overridden)
         out = {
             "metric": METRIC, "value": main_r["value"], "unit": "MLUPS", "n_gpus": args.gpus, "steps": main_r["steps"],
             "warmup": args.warmup, "ms_per_step": main_r["ms"] / main_r["steps"], "higher_is_better": True,
@@ -535,6 +580,8 @@ def main():
             out["macro_on"] = macro_on
         if parity is not None:
             out["multirank_parity"] = parity
+        if "edge_wait" in main_r:
+            out["edge_wait"] = main_r["edge_wait"]
         if e2e is not None:
             out["e2e"] = e2e
         if secondary is not None:

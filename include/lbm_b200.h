@@ -189,10 +189,12 @@ int lbm_ipc_attach(LbmSim *sim, const LbmIpcBlob *up, const LbmIpcBlob *down);
 uint64_t lbm_launch_count(const LbmSim *sim);
 /* How many of those launches were two-update sweeps (k_frame2), i.e. advanced the lattice by two updates. */
 uint64_t lbm_fused_sweep_count(const LbmSim *sim);
-/* 1 if sweeps run the kernel instance with the inline masked path (more than 2 % of the slab's cells were not plain
- * fluid at the last reset / preset generation / full upload: porous media, many obstacles), else 0.  Both instances
- * produce identical results; LBM_FUSE_MASKED=0|1 in the environment overrides the choice (tests, A/B runs). */
+/* 1 if sweeps run the kernel instance with the inline masked path for cells next to solids (the default), 0 if
+ * LBM_FUSE_MASKED=0 was in the environment at lbm_create (A/B runs, tests).  Both instances produce identical results. */
 int lbm_sweep_uses_masked_path(const LbmSim *sim);
+/* Multi-slab diagnostics (synchronises): nanoseconds the edge CTAs of this slab have spent waiting for their neighbour
+ * slabs' progress flags since creation, summed over CTAs, and the number of such waits. */
+int lbm_edge_wait_stats(LbmSim *sim, uint64_t *total_ns, uint64_t *n_waits);
 /* Device time of the last lbm_step_n call in milliseconds, measured with CUDA events on the
  * handle's own stream (torch.cuda.Event only sees torch's current stream). */
 int lbm_last_step_n_ms(LbmSim *sim, float *ms);

@@ -151,5 +151,6 @@ unsafe extern "C" {
     pub fn lbm_fused_sweep_count(sim: *const LbmSim) -> u64;
     pub fn lbm_sweep_uses_masked_path(sim: *const LbmSim) -> c_int;
     pub fn lbm_last_step_n_ms(sim: *mut LbmSim, ms: *mut f32) -> c_int;
+    pub fn lbm_edge_wait_stats(sim: *mut LbmSim, total_ns: *mut u64, n_waits: *mut u64) -> c_int;
     pub fn lbm_stream(sim: *mut LbmSim) -> *mut c_void;
 }

@@ -92,6 +92,7 @@ PROTOTYPES = {
     "lbm_fused_sweep_count": (_u64, [_H]),
     "lbm_sweep_uses_masked_path": (C.c_int, [_H]),
     "lbm_last_step_n_ms": (C.c_int, [_H, C.POINTER(_f32)]),
+    "lbm_edge_wait_stats": (C.c_int, [_H, C.POINTER(_u64), C.POINTER(_u64)]),
     "lbm_stream": (_vp, [_H]),
     # host-side mirrors
     "lbm_sweep_blocks": (_i32, [_i32, _i32, _vp, _i32, C.POINTER(_i32)]),

@@ -102,8 +102,7 @@ struct LbmSim {
     bool fuse_blocked = false;             // a ring cell would pull a stale value out of a solid (see k_ring_check)
     bool ring_check_needed = false;
     bool mask_written_since_reset = false;
-    bool use_masked = false;               // sweep kernel instance with the inline masked path (choose_masked)
-    unsigned long long *d_non_plain = nullptr;
+    bool use_masked = true;                // sweep kernel instance with the inline masked path (LBM_FUSE_MASKED=0: without)
     bool mixed_dirty = false;              // the mask changed: the mixed-warp list is rebuilt before the next single update
     bool halo_retire_pending = false;      // multi-slab: armed force cells in the info halo rows retire when the countdown ends
     // pinned staging ring of lbm_write_lattice_info: the caller's bytes are copied here and travel asynchronously, so
@@ -173,34 +172,15 @@ void invalidate_step_graphs(LbmSim *s);
 // back here.  The mixed-warp list of the single-update kernels is rebuilt lazily (ensure_mixed), and only the graphs
 // that contain those kernels are dropped — a two-update sweep does not depend on the mask geometry.
 // want_armed: also collect the largest armed block_iter of the rows into d_fuse_flags[0] (read by the caller).
-// A derive over the whole slab (reset, preset generation, an upload of most of the mask) also counts the non-plain
-// cells and reads the count back (those calls are heavyweight anyway): above kMaskedShare of the slab the sweeps use the
-// kernel instance with the inline masked path (see k_frame2).
-constexpr double kMaskedShare = 0.02;
-
 int derive_rows(LbmSim *s, int l0, int l1, bool want_armed = false) {
     l0 = std::max(l0, 0);
     l1 = std::min(l1, s->P.h);
     if (l0 >= l1) return LBM_OK;
     dim3 block(64, 4);
-    const bool whole = l0 == 0 && l1 == s->P.h;
     if (want_armed) CU(cudaMemsetAsync(s->d_fuse_flags, 0, sizeof(unsigned int), s->stream));
-    if (whole) CU(cudaMemsetAsync(s->d_non_plain, 0, sizeof(unsigned long long), s->stream));
-    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, want_armed ? s->d_fuse_flags : nullptr,
-                                                                        whole ? s->d_non_plain : nullptr);
+    k_derive<<<grid2d(s->P.nx, l1 - l0, block), block, 0, s->stream>>>(s->P, l0, l1, want_armed ? s->d_fuse_flags : nullptr);
     int rc = check_launch(s, "k_derive");
     if (rc) return rc;
-    if (whole) {
-        unsigned long long n = 0;
-        CU(cudaMemcpyAsync(&n, s->d_non_plain, sizeof(n), cudaMemcpyDeviceToHost, s->stream));
-        CU(cudaStreamSynchronize(s->stream));
-        const bool masked = getenv("LBM_FUSE_MASKED") ? atoi(getenv("LBM_FUSE_MASKED")) != 0
-                                                      : (double)n > kMaskedShare * (double)s->P.h * (double)s->P.nx;
-        if (masked != s->use_masked) {
-            s->use_masked = masked;
-            invalidate_graphs(s);
-        }
-    }
     if (s->cls_halo) {
         k_derive_halo<<<(s->P.pitch + 255) / 256, 256, 0, s->stream>>>(s->P, s->cls_halo, s->cls_halo + s->P.pitch);
         if ((rc = check_launch(s, "k_derive_halo"))) return rc;
@@ -677,7 +657,6 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
     cudaFree(s->d_fuse_flags);
-    cudaFree(s->d_non_plain);
     cudaFree(s->d_fuse_rows);
     cudaFree(s->cls_halo);
     cudaFree(s->mixed.list);
@@ -751,7 +730,6 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     CU(cudaMalloc(&P.nbr, cells));
     CU(cudaMemsetAsync(P.cls, CLS_SOLID, cells, s->stream));
     CU(cudaMemsetAsync(P.nbr, 0, cells, s->stream));
-    CU(cudaMalloc(&s->d_non_plain, sizeof(unsigned long long)));
     CU(cudaMalloc(&s->d_fuse_flags, 2 * sizeof(unsigned int)));
     CU(cudaMemsetAsync(s->d_fuse_flags, 0, 2 * sizeof(unsigned int), s->stream));
     if (d.world > 1) {
@@ -791,6 +769,7 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     // default FieldUniform (d2q9_node.rs:65-76); lbm_write_field_uniform may replace it
     lbm_field_uniform_new(d.nx, d.ny, (uint32_t)d.lattice_pixel_size, s->canvas_w, s->canvas_h, &s->field);
 
+    if (const char *e = getenv("LBM_FUSE_MASKED")) s->use_masked = atoi(e) != 0; // A/B runs, tests
     s->sync.flags = reinterpret_cast<unsigned int *>(s->arena + s->flag_off);
     s->sync.world = d.world;
     {
@@ -1613,6 +1592,18 @@ extern "C" int lbm_ipc_attach(LbmSim *s, const LbmIpcBlob *up, const LbmIpcBlob 
 extern "C" uint64_t lbm_launch_count(const LbmSim *s) { return s ? s->launches : 0; }
 extern "C" uint64_t lbm_fused_sweep_count(const LbmSim *s) { return s ? s->fused_sweeps : 0; }
 extern "C" int lbm_sweep_uses_masked_path(const LbmSim *s) { return s && s->use_masked ? 1 : 0; }
+
+extern "C" int lbm_edge_wait_stats(LbmSim *s, uint64_t *total_ns, uint64_t *n_waits) {
+    if (!s || !total_ns || !n_waits) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(s->device));
+    unsigned long long v[2] = {0, 0};
+    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpy(&v[0], s->sync.flags + 6, sizeof(v[0]), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&v[1], s->sync.flags + 8, sizeof(v[1]), cudaMemcpyDeviceToHost));
+    *total_ns = v[0];
+    *n_waits = v[1];
+    return LBM_OK;
+}
 
 extern "C" int lbm_last_step_n_ms(LbmSim *s, float *ms) {
     if (!s || !ms) return fail(s, LBM_ERR_INVALID_ARG, "null argument");

@@ -53,10 +53,7 @@ __global__ void __launch_bounds__(256) k_init(const __grid_constant__ SlabParams
 // Derived from the authoritative LatticeInfo buffer for owned rows [l0, l1).
 // armed (optional): receives the largest block_iter of the inlet / force cells seen (atomicMax) — the host
 // keeps the two-update kernel off while a countdown is running (collide_stream.wgsl:55-62).
-// non_plain (optional): receives the number of cells whose class is not plain fluid (the host picks the sweep kernel
-// instance from it).
-__global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabParams P, int l0, int l1, unsigned int *armed,
-                                                unsigned long long *non_plain) {
+__global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabParams P, int l0, int l1, unsigned int *armed) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int l = l0 + blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= P.nx || l >= l1) return;
@@ -106,10 +103,6 @@ __global__ void __launch_bounds__(256) k_derive(const __grid_constant__ SlabPara
     const size_t cl = (size_t)l * P.pitch + x;
     P.cls[cl] = c;
     P.nbr[cl] = nb;
-    if (non_plain) {
-        const unsigned int m = __ballot_sync(__activemask(), c != CLS_FLUID);
-        if (m && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(non_plain, (unsigned long long)__popc(m));
-    }
 }
 
 // ------------------------------------------------------------------ class rows of the two halo rows

@@ -46,6 +46,8 @@ inline long getpid_portable() { return (long)getpid(); }
 //   [2] edge-CTA arrival counter of the running step
 //   [3] sticky error word (1 = a wait timed out)
 //   [4] steps completed by this slab (device-side, so that launches can be replayed from CUDA graphs)
+//   [6..7] u64: nanoseconds edge CTAs spent in wait_neighbours, summed over CTAs;  [8..9] u64: number of such waits
+//          (diagnostics for the scaling analysis: lbm_edge_wait_stats)
 struct StepSync {
     unsigned int *flags;          // own
     unsigned int *peer_flags[2];  // up / down neighbour's flag words (peer memory)
@@ -98,6 +100,8 @@ __device__ __forceinline__ void wait_neighbours(const StepSync &S) {
                 }
                 __nanosleep(200);
             }
+            atomicAdd(reinterpret_cast<unsigned long long *>(S.flags + 6), globaltimer_ns() - t0);
+            atomicAdd(reinterpret_cast<unsigned long long *>(S.flags + 8), 1ull);
         }
         __syncthreads();
     }

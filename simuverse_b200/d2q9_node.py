@@ -269,6 +269,12 @@ class D2Q9Node:
         check(lib.lbm_last_step_n_ms(self._h, C.byref(ms)), self._h)
         return ms.value
 
+    def edge_wait_stats(self):
+        """(nanoseconds summed over edge CTAs, number of waits) spent waiting for the neighbour slabs so far."""
+        ns, n = C.c_uint64(), C.c_uint64()
+        check(lib.lbm_edge_wait_stats(self._h, C.byref(ns), C.byref(n)), self._h)
+        return ns.value, n.value
+
     def refresh_previous(self):
         """Recompute the buffer a two-update sweep left two updates behind (collective on multi-slab lattices)."""
         check(lib.lbm_refresh_previous(self._h), self._h)

@@ -105,8 +105,8 @@ CASES = [
 @pytest.mark.parametrize("masked", [0, 1])
 @pytest.mark.parametrize("nx,ny,preset,solid", CASES)
 def test_sweeps_equal_single_updates_and_oracle(orc, nx, ny, preset, solid, masked, monkeypatch):
-    """Both instances of the sweep kernel — with and without the inline masked path for pairs next to solids (chosen by
-    the host from the share of non-plain cells; forced here) — on every case."""
+    """Both instances of the sweep kernel — with (default) and without the inline masked path for pairs next to solids —
+    on every case."""
     monkeypatch.setenv("LBM_FUSE_MASKED", str(masked))
     info = random_mask(orc, nx, ny, preset, seed=nx * 1000 + ny, solid=solid) if solid > 0 else \
         orc.init_lattice_material(nx, ny, preset)
@@ -128,17 +128,14 @@ def test_sweeps_equal_single_updates_and_oracle(orc, nx, ny, preset, solid, mask
     b.close()
 
 
-def test_sweep_kernel_instance_follows_the_mask(orc):
-    """> 2 % non-plain cells at the last reset: the instance with the masked path; a sparse channel: the plain one."""
-    for nx, ny, solid, want in [(2048, 1024, 0.0, False), (512, 256, 0.30, True), (512, 256, 0.01, True)]:
-        info = random_mask(orc, nx, ny, W.CUSTOM, seed=5, solid=solid, forces=0) if solid else orc.init_lattice_material(nx, ny, W.CUSTOM)
-        a = node_for(nx, ny, W.CUSTOM, info)
-        assert a.sweep_uses_masked_path == want, (solid, a.sweep_uses_masked_path)
-        a.close()
-    a = sb.D2Q9Node((16384, 16384), setting(W.POISEUILLE), lattice=(8192, 8192), device_preset=sb.PRESET_POROUS)
+def test_sweep_kernel_instance_default_and_override(orc, monkeypatch):
+    """The instance with the inline masked path is the default; LBM_FUSE_MASKED=0 selects the other one."""
+    info = orc.init_lattice_material(256, 128, W.CUSTOM)
+    a = node_for(256, 128, W.CUSTOM, info)
     assert a.sweep_uses_masked_path
     a.close()
-    a = sb.D2Q9Node((8192, 8192), setting(W.POISEUILLE), lattice=(4096, 4096), device_preset=W.POISEUILLE)
+    monkeypatch.setenv("LBM_FUSE_MASKED", "0")
+    a = node_for(256, 128, W.CUSTOM, info)
     assert not a.sweep_uses_masked_path
     a.close()
 
