@@ -189,8 +189,11 @@ class FluidSimulator {
         node_.reset_lattice_info();
         pre_pos_ = {};
     }
-    // fluid_simulator.rs:217-232: one frame = step(0), particles, step(1), particles
-    void compute() {
+    // fluid_simulator.rs:217-232: one frame = step(0), particles, step(1), particles — inside the library ONE
+    // two-update sweep that stores the macro texture of both updates, then the two particle passes (same results)
+    void compute(int32_t n_frames = 1) { check(lbm_compute_frames(node_.handle(), n_frames), node_.handle()); }
+    // the same frame issued call by call, as the reference records it (single-update kernels)
+    void compute_by_passes() {
         node_.compute_by_pass(0);
         check(lbm_particles_update(node_.handle()), node_.handle());
         node_.compute_by_pass(1);

@@ -206,6 +206,10 @@ void *lbm_stream(LbmSim *sim);
  * number of blocks (0 on bad arguments / too small cap), *n_edge = how many leading blocks hold the slab's first / last
  * rows.  No reference counterpart; exported so that the cutting rules are testable without a GPU. */
 int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_t cap, int32_t *n_edge);
+/* Same with the last tail_rows rows cut into blocks of tail_rows_per_block rows (dispatched last: short work items at the
+ * end of a grid of few waves). */
+int32_t lbm_sweep_blocks_tail(int32_t h, int32_t rows_per_block, int32_t tail_rows, int32_t tail_rows_per_block,
+                              int32_t *out, int32_t cap, int32_t *n_edge);
 /* fluid/mod.rs:31-55 LbmUniform::new */
 void  lbm_uniform_new(float tau, int32_t fluid_ty, int32_t soa_offset, LbmUniform *out);
 /* d2q9_node.rs:50, fluid_simulator.rs:177 */

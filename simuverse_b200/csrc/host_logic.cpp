@@ -258,12 +258,21 @@ extern "C" void lbm_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas
 // h-1, then the rest top to bottom (on a multi-slab lattice the first two are the ones that talk to the neighbour
 // slabs, lbm_fused.cuh).  A 1-row remainder is merged into its predecessor, so that the last block always holds
 // the slab's last two rows.  out: (y0, y1) pairs; returns the number of blocks, *n_edge = 1 or 2.
-extern "C" int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_t cap, int32_t *n_edge) {
+// lbm_sweep_blocks_tail: the last tail_rows rows are cut into shorter blocks (tail_rows_per_block).  They are the last
+// CTAs dispatched: a grid of only a few waves then ends with short work items instead of a ragged last wave.
+extern "C" int32_t lbm_sweep_blocks_tail(int32_t h, int32_t rows_per_block, int32_t tail_rows, int32_t tail_rows_per_block,
+                                         int32_t *out, int32_t cap, int32_t *n_edge) {
     if (h < 1 || rows_per_block < 1 || !out) return 0;
+    if (tail_rows < 0 || tail_rows >= h || tail_rows_per_block < 1) tail_rows = 0;
     std::vector<int32_t> lo_, hi_;
-    for (int32_t y = 0; y < h; y += rows_per_block) {
+    const int32_t body = h - tail_rows;
+    for (int32_t y = 0; y < body; y += rows_per_block) {
         lo_.push_back(y);
-        hi_.push_back(y + rows_per_block < h ? y + rows_per_block : h);
+        hi_.push_back(y + rows_per_block < body ? y + rows_per_block : body);
+    }
+    for (int32_t y = body; y < h; y += tail_rows_per_block) {
+        lo_.push_back(y);
+        hi_.push_back(y + tail_rows_per_block < h ? y + tail_rows_per_block : h);
     }
     if (lo_.size() > 1 && hi_.back() - lo_.back() < 2) {
         lo_.pop_back();
@@ -278,4 +287,8 @@ extern "C" int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *
     for (int32_t i = 1; i + 1 < n; i++) { out[2 * k] = lo_[i]; out[2 * k + 1] = hi_[i]; k++; }
     if (n_edge) *n_edge = n > 1 ? 2 : 1;
     return n;
+}
+
+extern "C" int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_t cap, int32_t *n_edge) {
+    return lbm_sweep_blocks_tail(h, rows_per_block, 0, 1, out, cap, n_edge);
 }

@@ -377,10 +377,31 @@ int fuse_geometry(LbmSim *s) {
     int H0 = std::min(fixed0, H); // the first strip column (the inlet column of a channel) in short blocks: see k_frame2
     if (s->d.world > 1) { H = std::max(H, 2); H0 = std::max(H0, 2); } // a neighbour reads two rows: one block must hold both
     // blocks of height `hh` in dispatch order (lbm_sweep_blocks, host_logic.cpp)
+    // Tail shaping: when the grid is only a few waves long, the rows dispatched last — about one wave of CTAs — are cut
+    // at half height, so that the sweep ends with short work items instead of a ragged last wave (4096^2: 6.6 waves,
+    // SMs active 91 % of the launch without it).  LBM_FUSE_TAIL=0 turns it off.
+    int tail_rows = 0, tail_div = 2;
+    double tail_waves = 1.0;
+    {
+        int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const long long resident = (long long)sms * per_sm;
+        const long long blocks = (long long)g.ctas_x * ((h + H - 1) / H);
+        const bool on = getenv("LBM_FUSE_TAIL") ? atoi(getenv("LBM_FUSE_TAIL")) != 0 : true;
+        if (const char *e = getenv("LBM_FUSE_TAIL_WAVES")) tail_waves = atof(e);
+        if (const char *e = getenv("LBM_FUSE_TAIL_DIV")) tail_div = std::max(2, atoi(e));
+        if (on && fixed <= 0 && g.ctas_x > 1 && H >= 8 && blocks > resident && blocks < 24 * resident) {
+            // short blocks for about tail_waves waves of CTAs
+            const long long tail_blocks = (long long)(tail_waves * (double)resident / (double)(g.ctas_x - 1)) + 1;
+            tail_rows = (int)(((tail_blocks * (H / tail_div) + H - 1) / H) * H);
+            if (tail_rows >= h / 2) tail_rows = 0;
+        }
+    }
     auto cut = [&](int hh, std::vector<int2> &out) {
-        std::vector<int32_t> flat(2 * ((size_t)h / std::max(hh, 1) + 2));
+        const int th = std::max(hh / tail_div, 2);
+        std::vector<int32_t> flat(2 * ((size_t)h / std::max(std::min(hh, th), 1) + 4));
         int32_t n_edge = 0;
-        const int n = lbm_sweep_blocks(h, hh, flat.data(), (int32_t)(flat.size() / 2), &n_edge);
+        const int n = lbm_sweep_blocks_tail(h, hh, hh == H ? tail_rows : 0, th, flat.data(), (int32_t)(flat.size() / 2), &n_edge);
         for (int k = 0; k < n; k++) out.push_back(make_int2(flat[2 * k], flat[2 * k + 1]));
         return (int)n_edge;
     };

@@ -4,6 +4,8 @@
 // RGBA16F macro texture the step writes (f16-quantised, like textureLoad in the reference).
 #pragma once
 
+#include <stdlib.h>
+
 #include "lbm_device.cuh"
 
 namespace lbm {
@@ -34,7 +36,13 @@ __global__ void __launch_bounds__(256) k_particle_update(const __half *__restric
     const int gy = blockIdx.y * blockDim.y + threadIdx.y;
     if (gx >= pu.num[0] || gy >= pu.num[1]) return;
     const size_t p_index = (size_t)gx + (size_t)gy * pu.num[0];
-    TrajectoryParticle p = particles[p_index];
+    // 24-byte record, 8-byte aligned: three 64-bit accesses each way
+    TrajectoryParticle p;
+    {
+        const float2 *src = reinterpret_cast<const float2 *>(particles + p_index);
+        const float2 a = src[0], b = src[1], c = src[2];
+        p.pos[0] = a.x; p.pos[1] = a.y; p.pos_initial[0] = b.x; p.pos_initial[1] = b.y; p.life_time = c.x; p.fade = c.y;
+    }
     if (p.life_time <= 0.1f) {
         p.fade = 0.0f;
         p.pos[0] = p.pos_initial[0];
@@ -78,7 +86,12 @@ __global__ void __launch_bounds__(256) k_particle_update(const __half *__restric
                 }
         }
     }
-    particles[p_index] = p;
+    {
+        float2 *dst = reinterpret_cast<float2 *>(particles + p_index);
+        dst[0] = make_float2(p.pos[0], p.pos[1]);
+        // pos_initial never changes
+        dst[2] = make_float2(p.life_time, p.fade);
+    }
 }
 
 // curl_update.wgsl:12-33 — derived field of the macro texture (the reference's `_curl_cal_node`).  One thread per
@@ -115,8 +128,19 @@ __global__ void __launch_bounds__(256) k_canvas_fade(Pixel *canvas, size_t n, fl
 inline cudaError_t launch_particle_update(const SlabParams &P, const FieldUniform &field, const ParticleUniform &pu,
                                           TrajectoryParticle *particles, Pixel *canvas, cudaStream_t stream) {
     if (pu.num[0] <= 0 || pu.num[1] <= 0) return cudaSuccess;
-    dim3 block(16, 16); // particle_update.wgsl:55
-    dim3 grid((pu.num[0] + 15) / 16, (pu.num[1] + 15) / 16);
+    // The reference dispatches (16, 16) workgroups (particle_update.wgsl:55).  Here a warp is a tile of 4 consecutive
+    // particles x 8 rows of the particle grid: particles are seeded column by column (lib.rs:275-316: x outer, y inner),
+    // so consecutive indices sit in different lattice ROWS (64 KB apart at nx = 8192) while a step of num.x in the index
+    // is the next particle in the same row; the 4 x 8 tile keeps a warp's texel fetches and canvas splats within a few
+    // rows (DRAM pages) instead of 16, and its particle records in 96-byte runs.  LBM_PARTICLE_BLOCK_X overrides (A/B).
+    static int bx = 0;
+    if (!bx) {
+        const char *e = getenv("LBM_PARTICLE_BLOCK_X");
+        bx = e ? atoi(e) : 4;
+        if (bx != 4 && bx != 8 && bx != 16 && bx != 32) bx = 4;
+    }
+    dim3 block(bx, 256 / bx);
+    dim3 grid((pu.num[0] + block.x - 1) / block.x, (pu.num[1] + block.y - 1) / block.y);
     k_particle_update<<<grid, block, 0, stream>>>(P.macro16, P.nx, P.h, field, pu, P.k.fluid_ty == 0, particles, canvas);
     return cudaGetLastError();
 }

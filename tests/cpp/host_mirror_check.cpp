@@ -35,7 +35,21 @@ int main() {
     sim.compute();
     double mass = 0.0;
     lbm::check(lbm_total_mass(sim.fluid_compute_node().handle(), lbm_swap_index(sim.fluid_compute_node().handle()), &mass));
-    std::printf("HOST_MIRROR_OK gpu mass=%.6f launches=%llu\n", mass,
-                (unsigned long long)lbm_launch_count(sim.fluid_compute_node().handle()));
+    // the same session with every frame issued call by call (single-update kernels): identical distributions
+    lbm::FluidSimulator ref({1200, 750}, lbm::SettingObj{});
+    ref.compute_by_passes();
+    ref.on_click({700.0f, 400.0f});
+    ref.touch_begin();
+    ref.touch_move({300.0f, 300.0f});
+    ref.touch_move({340.0f, 310.0f});
+    ref.compute_by_passes();
+    std::vector<float> a(9 * 600 * 375), b(a.size());
+    LbmSim *ha = sim.fluid_compute_node().handle(), *hb = ref.fluid_compute_node().handle();
+    lbm::check(lbm_read_distributions(ha, lbm_swap_index(ha), a.data()), ha);
+    lbm::check(lbm_read_distributions(hb, lbm_swap_index(hb), b.data()), hb);
+    if (std::memcmp(a.data(), b.data(), a.size() * sizeof(float)) != 0) return 8;
+    if (lbm_fused_sweep_count(ha) == 0 || lbm_fused_sweep_count(hb) != 0) return 9;
+    std::printf("HOST_MIRROR_OK gpu mass=%.6f launches=%llu sweeps=%llu\n", mass,
+                (unsigned long long)lbm_launch_count(ha), (unsigned long long)lbm_fused_sweep_count(ha));
     return mass > 2.0e5 && mass < 2.2e5 ? 0 : 7;
 }

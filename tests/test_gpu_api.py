@@ -283,3 +283,20 @@ def test_pipelined_macro_readback(orc):
     for which in (0, 1):
         assert_bits_equal(node.read_distributions(which), sim.distributions(which), "state")
     node.close()
+
+
+def test_cpp_host_mirror_on_the_gpu(tmp_path):
+    """include/d2q9_node.hpp (the C++ mirror of D2Q9Node / FluidSimulator, the language a compiled host would use in
+    place of the unbuildable Rust shim) through a session of frames, a click and a drag: frames issued through
+    lbm_compute_frames (sweeps) and call by call (single updates) leave identical distributions."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_mirror_check"
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "host_mirror_check.cpp"), sb.LIB_PATH,
+                           "-Wl,-rpath," + os.path.dirname(sb.LIB_PATH), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "HOST_MIRROR_OK gpu" in r.stdout, r.stdout + r.stderr

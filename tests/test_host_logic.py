@@ -220,3 +220,30 @@ def test_sweep_row_blocks_cover_every_row_once(h, rows):
         assert blocks[1][1] == h and blocks[1][1] - blocks[1][0] >= 2 or h < 2
         assert [b for b in blocks[2:]] == covered[1:-1], "interior blocks top to bottom"
     assert lib.lbm_sweep_blocks(h, rows, out, 0, C.byref(n_edge)) == 0  # cap too small: refused, nothing written
+
+
+@pytest.mark.parametrize("h,rows,tail,tail_rows", [(4096, 16, 352, 8), (2048, 32, 192, 16), (100, 8, 24, 4), (64, 16, 0, 8),
+                                                   (64, 16, 64, 8), (33, 8, 9, 2)])
+def test_sweep_row_blocks_with_a_short_tail(h, rows, tail, tail_rows):
+    """lbm_sweep_blocks_tail: same partition rules; the last `tail` rows come in shorter blocks, dispatched last."""
+    import ctypes as C
+
+    from simuverse_b200._capi import lib
+
+    cap = h // min(rows, tail_rows) + 4
+    out = (C.c_int32 * (2 * cap))()
+    n_edge = C.c_int32(0)
+    n = lib.lbm_sweep_blocks_tail(h, rows, tail, tail_rows, out, cap, C.byref(n_edge))
+    assert n >= 1
+    blocks = [(out[2 * k], out[2 * k + 1]) for k in range(n)]
+    covered = sorted(blocks)
+    assert covered[0][0] == 0 and covered[-1][1] == h
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert blocks[0][0] == 0 and (n == 1 or blocks[1][1] == h)
+    assert [b for b in blocks[2:]] == covered[1:-1]
+    eff_tail = tail if 0 <= tail < h else 0
+    for y0, y1 in covered:
+        limit = tail_rows if y0 >= h - eff_tail else rows
+        assert y1 - y0 <= limit + 1  # (+1: a 1-row remainder is merged into its predecessor)
+    if eff_tail:
+        assert any(y0 >= h - eff_tail and y1 - y0 <= tail_rows for y0, y1 in covered)
