@@ -128,16 +128,15 @@ __global__ void __launch_bounds__(256) k_canvas_fade(Pixel *canvas, size_t n, fl
 inline cudaError_t launch_particle_update(const SlabParams &P, const FieldUniform &field, const ParticleUniform &pu,
                                           TrajectoryParticle *particles, Pixel *canvas, cudaStream_t stream) {
     if (pu.num[0] <= 0 || pu.num[1] <= 0) return cudaSuccess;
-    // The reference dispatches (16, 16) workgroups (particle_update.wgsl:55).  Here a warp is a tile of 4 consecutive
-    // particles x 8 rows of the particle grid: particles are seeded column by column (lib.rs:275-316: x outer, y inner),
-    // so consecutive indices sit in different lattice ROWS (64 KB apart at nx = 8192) while a step of num.x in the index
-    // is the next particle in the same row; the 4 x 8 tile keeps a warp's texel fetches and canvas splats within a few
-    // rows (DRAM pages) instead of 16, and its particle records in 96-byte runs.  LBM_PARTICLE_BLOCK_X overrides (A/B).
+    // (16, 16) threads per block like the reference's workgroups (particle_update.wgsl:55).  Other warp tiles of the particle
+    // grid (4 x 8, 8 x 4, 32 x 1; LBM_PARTICLE_BLOCK_X) were measured on 1000 x 1000 tracers over the 8192^2 porous field:
+    // 51.7 - 53.8 us per pass whatever the shape — the pass is bound by the latency of its scattered texel fetches and
+    // canvas splats, 6 % of a frame (profiles/r02_masked_path_ab.md).
     static int bx = 0;
     if (!bx) {
         const char *e = getenv("LBM_PARTICLE_BLOCK_X");
-        bx = e ? atoi(e) : 4;
-        if (bx != 4 && bx != 8 && bx != 16 && bx != 32) bx = 4;
+        bx = e ? atoi(e) : 16;
+        if (bx != 4 && bx != 8 && bx != 16 && bx != 32) bx = 16;
     }
     dim3 block(bx, 256 / bx);
     dim3 grid((pu.num[0] + block.x - 1) / block.x, (pu.num[1] + block.y - 1) / block.y);
