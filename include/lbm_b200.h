@@ -210,6 +210,12 @@ int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_
  * end of a grid of few waves). */
 int32_t lbm_sweep_blocks_tail(int32_t h, int32_t rows_per_block, int32_t tail_rows, int32_t tail_rows_per_block,
                               int32_t *out, int32_t cap, int32_t *n_edge);
+/* The schedule verdict of a lbm_write_lattice_info call, as a pure function of its arguments (every rank of a multi-slab
+ * lattice computes it from the same bytes): *armed = largest block_iter > 0 of a written inlet / force cell,
+ * *border_solid = 1 if a solid is written within one cell of the outer ring.  Returns 0 (and the conservative answer)
+ * for writes that are not LatticeInfo-aligned.  No reference counterpart; exported for CPU tests. */
+int32_t lbm_scan_lattice_info_write(int32_t nx, int32_t ny, uint64_t byte_offset, const void *src, uint64_t nbytes,
+                                    int32_t *armed, int32_t *border_solid);
 /* fluid/mod.rs:31-55 LbmUniform::new */
 void  lbm_uniform_new(float tau, int32_t fluid_ty, int32_t soa_offset, LbmUniform *out);
 /* d2q9_node.rs:50, fluid_simulator.rs:177 */

@@ -147,6 +147,7 @@ unsafe extern "C" {
 
     pub fn lbm_refresh_previous(sim: *mut LbmSim) -> i32;
     pub fn lbm_sweep_blocks(h: i32, rows_per_block: i32, out: *mut i32, cap: i32, n_edge: *mut i32) -> i32;
+    pub fn lbm_scan_lattice_info_write(nx: i32, ny: i32, byte_offset: u64, src: *const c_void, nbytes: u64, armed: *mut i32, border_solid: *mut i32) -> i32;
     pub fn lbm_sweep_blocks_tail(h: i32, rows_per_block: i32, tail_rows: i32, tail_rows_per_block: i32, out: *mut i32, cap: i32, n_edge: *mut i32) -> i32;
     pub fn lbm_launch_count(sim: *const LbmSim) -> u64;
     pub fn lbm_fused_sweep_count(sim: *const LbmSim) -> u64;

@@ -97,6 +97,7 @@ PROTOTYPES = {
     # host-side mirrors
     "lbm_sweep_blocks": (_i32, [_i32, _i32, _vp, _i32, C.POINTER(_i32)]),
     "lbm_sweep_blocks_tail": (_i32, [_i32, _i32, _i32, _i32, _vp, _i32, C.POINTER(_i32)]),
+    "lbm_scan_lattice_info_write": (_i32, [_i32, _i32, _u64, _vp, _u64, C.POINTER(_i32), C.POINTER(_i32)]),
     "lbm_uniform_new": (None, [_f32, _i32, _i32, C.POINTER(LbmUniform)]),
     "lbm_tau_from_viscosity": (_f32, [_f32]),
     "lbm_field_uniform_new": (None, [_i32, _i32, _u32, _i32, _i32, C.POINTER(FieldUniform)]),

@@ -292,3 +292,32 @@ extern "C" int32_t lbm_sweep_blocks_tail(int32_t h, int32_t rows_per_block, int3
 extern "C" int32_t lbm_sweep_blocks(int32_t h, int32_t rows_per_block, int32_t *out, int32_t cap, int32_t *n_edge) {
     return lbm_sweep_blocks_tail(h, rows_per_block, 0, 1, out, cap, n_edge);
 }
+
+// What the bytes of a lbm_write_lattice_info call mean for the step schedule (lbm_b200.cu).  Every rank of a multi-slab
+// lattice is handed the same call and must reach the same verdict without communication, so it is a pure function of
+// the arguments: *armed = the largest block_iter > 0 of an inlet / force cell among the written cells (single updates
+// while it counts down, collide_stream.wgsl:55-62), *border_solid = 1 if a solid (material 2 or 4) is written within
+// one cell of the outer ring — only there can a solid painted over live fluid leave a value that a ring cell keeps
+// pulling (boundary.wgsl:19 never rewrites those slots).  Writes that are not LatticeInfo-aligned cannot be parsed:
+// they report the conservative answer (border_solid = 1) and return 0.
+extern "C" int32_t lbm_scan_lattice_info_write(int32_t nx, int32_t ny, uint64_t byte_offset, const void *src, uint64_t nbytes,
+                                               int32_t *armed, int32_t *border_solid) {
+    if (armed) *armed = 0;
+    if (border_solid) *border_solid = 1;
+    if (nx < 1 || ny < 1 || (!src && nbytes)) return 0;
+    if (byte_offset % sizeof(LatticeInfo) != 0 || nbytes % sizeof(LatticeInfo) != 0) return 0;
+    const LatticeInfo *cells = static_cast<const LatticeInfo *>(src);
+    const uint64_t n = nbytes / sizeof(LatticeInfo);
+    const uint64_t idx = byte_offset / sizeof(LatticeInfo);
+    int32_t x = static_cast<int32_t>(idx % static_cast<uint64_t>(nx)), y = static_cast<int32_t>(idx / static_cast<uint64_t>(nx));
+    int32_t a = 0, b = 0;
+    for (uint64_t k = 0; k < n; k++) {
+        const int32_t m = cells[k].material;
+        if ((m == LATTICE_INLET || m == LATTICE_EXTERNAL_FORCE) && cells[k].block_iter > a) a = cells[k].block_iter;
+        if ((m == LATTICE_BOUNDARY || m == LATTICE_OBSTACLE) && (x <= 1 || x >= nx - 2 || y <= 1 || y >= ny - 2)) b = 1;
+        if (++x == nx) { x = 0; y++; }
+    }
+    if (armed) *armed = a;
+    if (border_solid) *border_solid = b;
+    return 1;
+}

@@ -864,18 +864,9 @@ namespace {
 struct WriteScan { int32_t armed; bool border_solid; };
 
 WriteScan scan_written_cells(int nx, int ny, uint64_t byte_offset, const void *src, uint64_t nbytes) {
-    WriteScan w{0, false};
-    const LatticeInfo *cells = static_cast<const LatticeInfo *>(src);
-    const uint64_t n = nbytes / sizeof(LatticeInfo);
-    uint64_t idx = byte_offset / sizeof(LatticeInfo);
-    int x = (int)(idx % (uint64_t)nx), y = (int)(idx / (uint64_t)nx);
-    for (uint64_t k = 0; k < n; k++) {
-        const int m = cells[k].material;
-        if ((m == 3 || m == 6) && cells[k].block_iter > w.armed) w.armed = cells[k].block_iter;
-        if ((m == 2 || m == 4) && (x <= 1 || x >= nx - 2 || y <= 1 || y >= ny - 2)) w.border_solid = true;
-        if (++x == nx) { x = 0; y++; }
-    }
-    return w;
+    int32_t armed = 0, border = 1;
+    lbm_scan_lattice_info_write(nx, ny, byte_offset, src, nbytes, &armed, &border); // host_logic.cpp (CPU-testable)
+    return WriteScan{armed, border != 0};
 }
 
 // Host bytes -> device through the pinned staging ring; returns without waiting for the device.  Small writes share

@@ -247,3 +247,47 @@ def test_sweep_row_blocks_with_a_short_tail(h, rows, tail, tail_rows):
         assert y1 - y0 <= limit + 1  # (+1: a 1-row remainder is merged into its predecessor)
     if eff_tail:
         assert any(y0 >= h - eff_tail and y1 - y0 <= tail_rows for y0, y1 in covered)
+
+
+def test_schedule_verdict_of_a_mask_write_is_a_function_of_its_bytes():
+    """lbm_scan_lattice_info_write: what every rank of a multi-slab lattice derives from a lbm_write_lattice_info call."""
+    import ctypes as C
+
+    from simuverse_b200 import wire as W
+    from simuverse_b200._capi import lib
+
+    nx, ny = 64, 40
+
+    def scan(off, cells):
+        cells = np.ascontiguousarray(cells, W.LATTICE_INFO_DTYPE)
+        a, b = C.c_int32(-7), C.c_int32(-7)
+        ok = lib.lbm_scan_lattice_info_write(nx, ny, off, W.ptr(cells), cells.nbytes, C.byref(a), C.byref(b))
+        return ok, a.value, b.value
+
+    bulk = np.zeros(3 * nx, W.LATTICE_INFO_DTYPE)
+    bulk["material"], bulk["block_iter"] = W.BULK, -1
+    assert scan(10 * nx * 16, bulk) == (1, 0, 0)                       # three interior rows of bulk
+    obst = bulk.copy()
+    obst["material"][nx + 20:nx + 30] = W.OBSTACLE                      # an obstacle in the interior
+    assert scan(10 * nx * 16, obst) == (1, 0, 0)
+    assert scan(0, obst) == (1, 0, 1)                                   # the same bytes at rows 0..2: row 1 is next to the ring
+    edge = bulk.copy()
+    edge["material"][nx + 1] = W.OBSTACLE                               # x = 1 of the second written row
+    assert scan(10 * nx * 16, edge) == (1, 0, 1)
+    edge = bulk.copy()
+    edge["material"][2 * nx - 2] = W.BOUNDARY                           # x = nx - 2
+    assert scan(10 * nx * 16, edge) == (1, 0, 1)
+    one = np.zeros(1, W.LATTICE_INFO_DTYPE)
+    one[0] = (W.EXTERNAL_FORCE, 90, 0.01, 0.0)                          # add_external_force: one armed cell
+    assert scan((20 * nx + 33) * 16, one) == (1, 90, 0)
+    one[0] = (W.EXTERNAL_FORCE, -1, 0.01, 0.0)                          # permanent force cell: nothing counts down
+    assert scan((20 * nx + 33) * 16, one) == (1, 0, 0)
+    one[0] = (W.OBSTACLE, -1, 0.0, 0.0)
+    assert scan(((ny - 2) * nx + 33) * 16, one) == (1, 0, 1)            # y = ny - 2
+    # a run that wraps from the end of one row to the start of the next: x restarts at 0
+    two = np.zeros(2, W.LATTICE_INFO_DTYPE)
+    two[:] = (W.BULK, -1, 0.0, 0.0)
+    two[1] = (W.OBSTACLE, -1, 0.0, 0.0)
+    assert scan((20 * nx + nx - 1) * 16, two) == (1, 0, 1)              # second cell is (x = 0, y = 21)
+    assert scan((20 * nx + 30) * 16 + 4, one)[0] == 0                   # misaligned: refused ...
+    assert scan((20 * nx + 30) * 16 + 4, one)[2] == 1                   # ... with the conservative verdict
