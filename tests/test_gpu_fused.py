@@ -333,3 +333,34 @@ def test_sweeps_on_slabs(orc, n_slabs):
         assert_bits_equal(got[live], want[live], f"after a mask write, buf{which}")
     assert all(n.fused_sweep_count == 36 for n in grp.nodes), [n.fused_sweep_count for n in grp.nodes]
     grp.close()
+
+
+@pytest.mark.parametrize("preset,solid", [(W.POISEUILLE, 0.30), (W.CUSTOM, 0.08)])
+def test_divergent_fallback_paths_on_a_wide_lattice(orc, preset, solid):
+    """4096 columns (18 CTA columns, a partial last strip), solids everywhere and hundreds of force cells whose numerators
+    hit the exact-division fallback (denormal components) or the signed-zero rule: every warp mixes the vector path,
+    the masked path, the out-of-line per-cell path (outer ring, first / last column) and the division fallback.  This
+    is the configuration on which a call from a divergent branch once made a lane run the row loop on its own."""
+    nx, ny = 4096, 96
+    rng = np.random.default_rng(17)
+    info = random_mask(orc, nx, ny, preset, seed=23, solid=solid, forces=0)
+    g = info.reshape(ny, nx)
+    ys, xs = np.nonzero(g["material"] == W.BULK)
+    for k in rng.choice(len(ys), size=400, replace=False):
+        vx = rng.choice([1e-39, -1e-40, -0.0, 0.02, -0.03])
+        vy = rng.choice([-1e-39, 3e-41, -0.0, 0.0, 0.04])
+        g[ys[k], xs[k]] = (W.EXTERNAL_FORCE, -1, vx, vy)
+    a = node_for(nx, ny, preset, info, flags=sb.FLAG_MACRO_EVERY_STEP)
+    b = node_for(nx, ny, preset, info, flags=sb.FLAG_MACRO_EVERY_STEP | sb.FLAG_NO_FUSE)
+    sim = oracle_for(orc, nx, ny, preset, info, threads=orc.lib().orc_get_max_threads())
+    for n in (6, 31):
+        a.step_n(n)
+        b.step_n(n)
+        sim.step(n)
+        cur = a.swap_index
+        assert_bits_equal(a.read_distributions(cur), b.read_distributions(cur), f"sweeps vs single updates after +{n}")
+        assert_bits_equal(a.read_distributions(cur), sim.distributions(cur), f"sweeps vs oracle after +{n}")
+        np.testing.assert_array_equal(a.read_macro_tex().view(np.uint16).reshape(-1), sim.macro_f16)
+    assert a.fused_sweep_count == 18 and b.fused_sweep_count == 0
+    a.close()
+    b.close()
