@@ -67,7 +67,9 @@ typedef enum LbmStatus {
 
 /* LbmDesc.flags */
 #define LBM_FLAG_MACRO_EVERY_STEP 0x1u /* write the RGBA16F macro texture in every step, like
-                                          collide_stream.wgsl:74 (needed by the tracer particles).
+                                          collide_stream.wgsl:74 (needed by the tracer particles).  Two-update
+                                          sweeps store it too (the texture between the two updates only when
+                                          tracer particles will read it).
                                           Off: the field is produced on demand by lbm_read_macro. */
 #define LBM_FLAG_KERNEL_GENERIC   0x2u /* force the one-thread-per-cell kernel (A/B testing) */
 #define LBM_FLAG_AA               0x8u /* AA-pattern in-place streaming: ONE copy of the distributions instead of
@@ -121,7 +123,10 @@ int lbm_write_uniform(LbmSim *sim, const LbmUniform *u);
 int lbm_write_field_uniform(LbmSim *sim, const FieldUniform *f);
 /* byte_offset/nbytes address the GLOBAL info buffer (nx*ny*16 bytes, row-major); a slab keeps
  * the part that intersects its rows and one halo row each side, so every rank may be handed
- * the same call. */
+ * the same call (on a multi-slab lattice it MUST be: the slabs derive from the bytes, each on its own, whether the
+ * next updates may run as two-update sweeps — see lbm_scan_lattice_info_write).  Cost: O(nbytes) on the host, no
+ * device round trip: the bytes are copied into a pinned staging ring (src may be reused at once) and uploaded
+ * asynchronously, ordered before the next step. */
 int lbm_write_lattice_info(LbmSim *sim, uint64_t byte_offset, const void *src, uint64_t nbytes);
 /* Same content as lbm_init_lattice_material / lbm_init_porous_material, generated on the
  * device (no host array, no upload).  kind: FieldAnimationType or LBM_PRESET_POROUS. */
@@ -132,7 +137,11 @@ int lbm_reset(LbmSim *sim);                         /* init.wgsl; next step read
 int lbm_step(LbmSim *sim, int32_t swap_index);      /* reads buffer swap_index, writes the other */
 int lbm_step_n(LbmSim *sim, int32_t n);             /* n steps alternating from lbm_swap_index */
 /* n_frames times FluidSimulator::compute (fluid_simulator.rs:217-232): step(0), particle update,
- * step(1), particle update (the particle updates only if the handle has tracer particles). */
+ * step(1), particle update (the particle updates only if the handle has tracer particles).  Unless something
+ * mutates between the two updates (a force cell counting down) a frame is ONE launch of the two-update sweep kernel,
+ * which also stores the macro texture of the second update — and of the first one into a second texture when tracer
+ * particles will sample it — followed by the two particle passes: particles only read the field, so the results are
+ * those of the reference's order, bit for bit. */
 int lbm_compute_frames(LbmSim *sim, int32_t n_frames);
 int lbm_swap_index(const LbmSim *sim);              /* buffer the next lbm_step_n step reads */
 /* After a two-update sweep the buffer that is not current holds the state two updates back; the calls that need what
