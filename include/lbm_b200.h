@@ -23,6 +23,8 @@
  *   lbm_read_macro             macro_tex (RGBA16F) contents              d2q9_node.rs:91-104
  *   lbm_read_curl              _curl_cal_node + curl_tex contents        fluid_simulator.rs:36-71,
  *                              = curl_update.wgsl:12-33
+ *   lbm_read_present           render_node (colour present of the field) fluid_simulator.rs:69-87
+ *                              = lbm/present.wgsl:21-46
  *   lbm_particles_update       particle_update_node.compute_by_pass      fluid_simulator.rs:225,229
  *                              = particle_update.wgsl:55-88
  *   lbm_read_distributions /   (no reference equivalent: can_read_back=false,
@@ -171,6 +173,17 @@ int lbm_read_macro_async(LbmSim *sim, void *dst);
  * shader's right / bottom taps are clamped to lattice_size — one past the last texel — where wgpu reads zeros; that is
  * reproduced.  Single-slab handles only (the reference is single-GPU and nothing consumes the texture). */
 int lbm_read_curl(LbmSim *sim, void *dst);
+/* The colour present of the field, lbm/present.wgsl:21-46 (`render_node`, fluid_simulator.rs:69-87; built by the
+ * reference, its draw call commented out at :243-244): the fragment outputs (r, g, b, a) as f32 for rows
+ * [row0, row0 + rows) of a FieldUniform.canvas_size target — hsv2rgb(curl.x, 0.6 + speed * 1.4, 0.6 + rho * 0.33), alpha
+ * = rho, the newest macro texture and its curl sampled through `bilinear_sampler` (ClampToEdge, linear) at
+ * uv = pixel centre / canvas_size.  The filter is WebGPU's formula in f32, one rounding per operation:
+ * c = uv * size - 0.5, i = floor(c), f = c - i, taps clamped to the edge, (1-fx)(1-fy) t00 + fx(1-fy) t10 + (1-fx) fy t01
+ * + fx fy t11 summed in that order (hardware samplers use fixed-point weights of unspecified width, so no GPU's output is
+ * bit-comparable with another's; the tests pin this arithmetic on the executed shader text).  The surface-format
+ * conversion of the render target is the caller's.  dst: rows * canvas_size[0] * 4 floats.
+ * Single-slab handles only. */
+int lbm_read_present(LbmSim *sim, int32_t row0, int32_t rows, float *dst);
 /* Owned rows of the info buffer including device-side block_iter/material mutation
  * (collide_stream.wgsl:55-62). dst: rows*nx LatticeInfo. */
 int lbm_read_lattice_info(LbmSim *sim, LatticeInfo *dst);

@@ -530,6 +530,66 @@ void orc_curl_update(int32_t nx, int32_t ny, const uint16_t *macro_f16, uint16_t
         }
 }
 
+/* ---------------------------------------------------------------- colour present of the field
+ * assets/wgsl/lbm/present.wgsl:21-46 (+ func/color_space_convert.wgsl:2-9, bufferless.vs.wgsl): the fragment shader of
+ * the reference's `render_node` (fluid_simulator.rs:69-87; its draw call is commented out, :243-244).  Per pixel of a
+ * canvas_size render target: macro = textureSample(macro_tex, uv), curl = textureSample(curl_tex, uv) through
+ * `bilinear_sampler` (util/load_texture.rs:229-243: ClampToEdge, linear), speed = |u.x| + |u.y|,
+ * colour = hsv2rgb(curl.x, 0.6 + speed * 1.4, 0.6 + rho * 0.33), alpha = rho.  The unused `canvas[p_index]` /
+ * `particle_uniform.color` reads and the dead `angle` (atan2) have no effect on the output.
+ * Fragment inputs: position = pixel centre, uv = position.xy / canvas_size.  The filter is the WebGPU formula evaluated
+ * in f32 with one rounding per operation (hardware samplers use fixed-point weights of unspecified width, so no
+ * implementation is bit-comparable with another; tests/wgsl_ref/runtime.py::textureSample states the same arithmetic). */
+static void orc_sample_bilinear(const uint16_t *tex, int32_t nx, int32_t ny, float u, float v, float out[4]) {
+    const float cx = u * (float)nx - 0.5f, cy = v * (float)ny - 0.5f;
+    const float fx0 = floorf(cx), fy0 = floorf(cy);
+    const float fx = cx - fx0, fy = cy - fy0;
+    int32_t x0 = (int32_t)fx0, y0 = (int32_t)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    x0 = x0 < 0 ? 0 : (x0 > nx - 1 ? nx - 1 : x0);
+    x1 = x1 < 0 ? 0 : (x1 > nx - 1 ? nx - 1 : x1);
+    y0 = y0 < 0 ? 0 : (y0 > ny - 1 ? ny - 1 : y0);
+    y1 = y1 < 0 ? 0 : (y1 > ny - 1 ? ny - 1 : y1);
+    const float gx = 1.0f - fx, gy = 1.0f - fy;
+    const float w00 = gx * gy, w10 = fx * gy, w01 = gx * fy, w11 = fx * fy;
+    for (int k = 0; k < 4; k++) {
+        float s = w00 * orc_tex(tex, nx, ny, x0, y0, k);
+        s = s + w10 * orc_tex(tex, nx, ny, x1, y0, k);
+        s = s + w01 * orc_tex(tex, nx, ny, x0, y1, k);
+        s = s + w11 * orc_tex(tex, nx, ny, x1, y1, k);
+        out[k] = s;
+    }
+}
+
+/* func/color_space_convert.wgsl:2-9.  K = (1, 2/3, 1/3, 3); fract(e) = e - floor(e); mix(a, b, t) = a*(1-t) + b*t */
+static void orc_hsv2rgb(float h, float s, float v, float rgb[3]) {
+    const float K[3] = {1.0f, 2.0f / 3.0f, 1.0f / 3.0f};
+    for (int k = 0; k < 3; k++) {
+        const float t = h + K[k];
+        const float p = fabsf((t - floorf(t)) * 6.0f - 3.0f);
+        float c = p - 1.0f;
+        c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c); /* clamp = min(max(c, 0), 1) */
+        rgb[k] = v * (1.0f * (1.0f - s) + c * s);
+    }
+}
+
+void orc_present(const FieldUniform *field, const uint16_t *macro_f16, const uint16_t *curl_f16, int32_t row0,
+                 int32_t rows, float *out_rgba) {
+    const int32_t nx = field->lattice_size[0], ny = field->lattice_size[1];
+    const int32_t W = field->canvas_size[0], H = field->canvas_size[1];
+#pragma omp parallel for schedule(static)
+    for (int32_t py = row0; py < row0 + rows; py++)
+        for (int32_t px = 0; px < W; px++) {
+            const float u = ((float)px + 0.5f) / (float)W, v = ((float)py + 0.5f) / (float)H;
+            float m[4], c[4], rgb[3];
+            orc_sample_bilinear(macro_f16, nx, ny, u, v, m);
+            orc_sample_bilinear(curl_f16, nx, ny, u, v, c);
+            const float speed = fabsf(m[0]) + fabsf(m[1]);
+            orc_hsv2rgb(c[0], 0.6f + speed * 1.4f, 0.6f + m[2] * 0.33f, rgb);
+            float *o = out_rgba + 4 * ((size_t)(py - row0) * (size_t)W + (size_t)px);
+            o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2]; o[3] = m[2];
+        }
+}
+
 void orc_canvas_fade(const FieldUniform *field, const ParticleUniform *pu, Pixel *canvas) {
     const size_t n = (size_t)field->canvas_size[0] * (size_t)field->canvas_size[1];
     for (size_t i = 0; i < n; i++) {

@@ -130,6 +130,13 @@ void orc_init_trajectory_particles(uint32_t canvas_w, uint32_t canvas_h, int32_t
  * (curl * 3.5 + 0.5, 0, 0, 0) as f16 texels. */
 void orc_curl_update(int32_t nx, int32_t ny, const uint16_t *macro_f16, uint16_t *curl_f16);
 
+/* assets/wgsl/lbm/present.wgsl:21-46 — the colour present of the field (`render_node`, fluid_simulator.rs:69-87; built by
+ * the reference, its draw call commented out at :243-244).  Fragment outputs (r, g, b, a) as f32 for canvas rows
+ * [row0, row0 + rows) of a canvas_size[0] x canvas_size[1] target: hsv2rgb(curl.x, 0.6 + speed * 1.4, 0.6 + rho * 0.33),
+ * alpha = rho, with macro / curl sampled bilinearly (ClampToEdge) at uv = pixel centre / canvas_size. */
+void orc_present(const FieldUniform *field, const uint16_t *macro_f16, const uint16_t *curl_f16, int32_t row0,
+                 int32_t rows, float *out_rgba);
+
 /* f64 sum of one distribution buffer (all 9 planes) — the "total mass" diagnostic. */
 double orc_total_mass(int32_t nx, int32_t ny, const float *buf);
 

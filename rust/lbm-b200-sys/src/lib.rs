@@ -131,6 +131,7 @@ unsafe extern "C" {
     pub fn lbm_read_macro(sim: *mut LbmSim, format: i32, dst: *mut c_void) -> c_int;
     pub fn lbm_read_macro_async(sim: *mut LbmSim, dst: *mut c_void) -> c_int;
     pub fn lbm_read_curl(sim: *mut LbmSim, dst: *mut c_void) -> c_int;
+    pub fn lbm_read_present(sim: *mut LbmSim, row0: i32, rows: i32, dst: *mut f32) -> c_int;
     pub fn lbm_read_lattice_info(sim: *mut LbmSim, dst: *mut LatticeInfo) -> c_int;
     pub fn lbm_total_mass(sim: *mut LbmSim, which: i32, out: *mut f64) -> c_int;
 

@@ -239,6 +239,13 @@ impl CudaD2Q9Node {
         self.check(unsafe { sys::lbm_read_curl(self.sim, dst.as_mut_ptr().cast()) })
     }
 
+    /// Fragment outputs of the reference's `render_node` (fluid_simulator.rs:69-87, lbm/present.wgsl:21-46) for rows
+    /// `row0 .. row0 + rows` of the canvas: `rows * canvas_width` RGBA f32 pixels.
+    pub fn read_present(&self, row0: u32, rows: u32, canvas_width: u32, dst: &mut [[f32; 4]]) -> LbmResult<()> {
+        assert_eq!(dst.len(), (rows * canvas_width) as usize);
+        self.check(unsafe { sys::lbm_read_present(self.sim, row0 as i32, rows as i32, dst.as_mut_ptr().cast()) })
+    }
+
     pub fn sync(&self) -> LbmResult<()> {
         self.check(unsafe { sys::lbm_sync(self.sim) })
     }

@@ -76,6 +76,7 @@ PROTOTYPES = {
     "lbm_read_macro": (C.c_int, [_H, _i32, _vp]),
     "lbm_read_macro_async": (C.c_int, [_H, _vp]),
     "lbm_read_curl": (C.c_int, [_H, _vp]),
+    "lbm_read_present": (C.c_int, [_H, _i32, _i32, _vp]),
     "lbm_read_lattice_info": (C.c_int, [_H, _vp]),
     "lbm_total_mass": (C.c_int, [_H, _i32, C.POINTER(C.c_double)]),
     "lbm_write_particle_uniform": (C.c_int, [_H, C.POINTER(ParticleUniform)]),

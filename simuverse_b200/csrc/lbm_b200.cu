@@ -59,6 +59,8 @@ struct LbmSim {
     float *scratch32 = nullptr; // 3 f32 planes for the on-demand macro read
     __half *scratch16 = nullptr; // RGBA16F texels for the on-demand macro read
     __half *curl16 = nullptr;    // RGBA16F texels of lbm_read_curl
+    float4 *present32 = nullptr; // fragment outputs of lbm_read_present (present_cap pixels)
+    size_t present_cap = 0;
     // second macro texture + copy stream for lbm_read_macro_async (pipelined field read-back)
     __half *macro_buf[2] = {nullptr, nullptr};
     int macro_cur = 0;
@@ -675,6 +677,7 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->scratch32);
     cudaFree(s->scratch16);
     cudaFree(s->curl16);
+    cudaFree(s->present32);
     cudaFree(s->scratch_dense);
     cudaFree(s->d_mass);
     cudaFree(s->d_fuse_flags);
@@ -1355,11 +1358,11 @@ extern "C" int lbm_read_macro(LbmSim *s, int32_t format, void *dst) {
     return LBM_OK;
 }
 
-// curl_update.wgsl over the newest macro texture (the step's own texture, or the on-demand one).
-extern "C" int lbm_read_curl(LbmSim *s, void *dst) {
-    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
-    if (s->d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "lbm_read_curl is single-slab only");
-    CU(cudaSetDevice(s->device));
+namespace {
+
+// curl_update.wgsl over the newest macro texture (the step's own texture, or the on-demand one) into s->curl16.
+// *tex_out: the macro texture it was computed from.
+int compute_curl(LbmSim *s, const __half **tex_out) {
     const SlabParams &P = s->P;
     const size_t n = (size_t)P.h * P.nx;
     const __half *tex = nullptr;
@@ -1392,7 +1395,50 @@ extern "C" int lbm_read_curl(LbmSim *s, void *dst) {
     k_curl<<<grid2d(P.nx, P.h, block), block, 0, s->stream>>>(tex, P.nx, P.h, s->curl16);
     int rc = check_launch(s, "k_curl");
     if (rc) return rc;
-    CU(cudaMemcpyAsync(dst, s->curl16, sizeof(__half) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    *tex_out = tex;
+    return LBM_OK;
+}
+
+}  // namespace
+
+extern "C" int lbm_read_curl(LbmSim *s, void *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (s->d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "lbm_read_curl is single-slab only");
+    CU(cudaSetDevice(s->device));
+    const __half *tex = nullptr;
+    int rc = compute_curl(s, &tex);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(dst, s->curl16, sizeof(__half) * 4 * (size_t)s->P.h * s->P.nx, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return LBM_OK;
+}
+
+// lbm/present.wgsl over the newest macro texture and its curl: fragment outputs of canvas rows [row0, row0 + rows).
+extern "C" int lbm_read_present(LbmSim *s, int32_t row0, int32_t rows, float *dst) {
+    if (!s || !dst) return fail(s, LBM_ERR_INVALID_ARG, "null argument");
+    if (s->d.world > 1) return fail(s, LBM_ERR_UNSUPPORTED, "lbm_read_present is single-slab only");
+    const int W = s->field.canvas_size[0], H = s->field.canvas_size[1];
+    if (W <= 0 || H <= 0) return fail(s, LBM_ERR_STATE, "FieldUniform.canvas_size is %dx%d", W, H);
+    if (row0 < 0 || rows < 0 || row0 > H || rows > H - row0)
+        return fail(s, LBM_ERR_INVALID_ARG, "rows [%d, %d + %d) outside the %d rows of the canvas", row0, row0, rows, H);
+    if (rows == 0) return LBM_OK;
+    CU(cudaSetDevice(s->device));
+    const __half *tex = nullptr;
+    int rc = compute_curl(s, &tex);
+    if (rc) return rc;
+    const size_t n = (size_t)rows * W;
+    if (s->present_cap < n) {
+        CU(cudaStreamSynchronize(s->stream));
+        cudaFree(s->present32);
+        s->present32 = nullptr;
+        s->present_cap = 0;
+        CU(cudaMalloc(&s->present32, sizeof(float4) * n));
+        s->present_cap = n;
+    }
+    dim3 block(64, 4);
+    k_present<<<grid2d(W, rows, block), block, 0, s->stream>>>(tex, s->curl16, s->P.nx, s->P.h, W, H, row0, rows, s->present32);
+    if ((rc = check_launch(s, "k_present"))) return rc;
+    CU(cudaMemcpyAsync(dst, s->present32, sizeof(float4) * n, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
     return LBM_OK;
 }

@@ -117,6 +117,74 @@ __global__ void __launch_bounds__(256) k_curl(const __half *__restrict__ macro16
     reinterpret_cast<uint2 *>(curl16)[(size_t)y * nx + x] = t;
 }
 
+// lbm/present.wgsl:21-46 — colour present of the field (fragment shader of the reference's `render_node`,
+// fluid_simulator.rs:69-87; built there, its draw call commented out at :243-244).  One thread per pixel of the
+// canvas_size target: position = pixel centre, uv = position / target size; macro and curl textures sampled through
+// `bilinear_sampler` (ClampToEdge, linear; util/load_texture.rs:229-243) with WebGPU's filter formula in f32, one
+// rounding per operation, taps summed in the order 00, 10, 01, 11 (hardware samplers use fixed-point weights of
+// unspecified width, so no two implementations are bit-comparable; this arithmetic is what include/lbm_b200.h defines
+// and the tests pin on the executed shader text).
+// colour = hsv2rgb(curl.x, 0.6 + speed * 1.4, 0.6 + rho * 0.33) (func/color_space_convert.wgsl:2-9), alpha = rho.
+// Bound by the 16 B per pixel it writes (one coalesced 128-bit store per thread); the 2 x 4 taps come out of L1 / L2.
+struct BilinearTaps { int o00, o10, o01, o11; float w00, w10, w01, w11; };
+
+__device__ __forceinline__ BilinearTaps bilinear_taps(int nx, int ny, float u, float v) {
+    const float cx = fsub(fmul(u, (float)nx), 0.5f), cy = fsub(fmul(v, (float)ny), 0.5f);
+    const float fx0 = floorf(cx), fy0 = floorf(cy);
+    const float fx = fsub(cx, fx0), fy = fsub(cy, fy0);
+    const int ix = (int)fx0, iy = (int)fy0;
+    const int x0 = min(max(ix, 0), nx - 1), x1 = min(max(ix + 1, 0), nx - 1);
+    const int y0 = min(max(iy, 0), ny - 1), y1 = min(max(iy + 1, 0), ny - 1);
+    const float gx = fsub(1.0f, fx), gy = fsub(1.0f, fy);
+    BilinearTaps t;
+    t.o00 = y0 * nx + x0; t.o10 = y0 * nx + x1; t.o01 = y1 * nx + x0; t.o11 = y1 * nx + x1;
+    t.w00 = fmul(gx, gy); t.w10 = fmul(fx, gy); t.w01 = fmul(gx, fy); t.w11 = fmul(fx, fy);
+    return t;
+}
+
+__device__ __forceinline__ float bilinear_mix(const BilinearTaps &t, float a, float b, float c, float d) {
+    float s = fmul(t.w00, a);
+    s = fadd(s, fmul(t.w10, b));
+    s = fadd(s, fmul(t.w01, c));
+    return fadd(s, fmul(t.w11, d));
+}
+
+__device__ __forceinline__ float hsv2rgb_channel(float h, float K, float s, float v) {
+    const float t = fadd(h, K);
+    const float p = fabsf(fsub(fmul(fsub(t, floorf(t)), 6.0f), 3.0f)); // |fract(h + K) * 6 - 3|
+    const float c = fminf(fmaxf(fsub(p, 1.0f), 0.0f), 1.0f);
+    return fmul(v, fadd(fsub(1.0f, s), fmul(c, s)));                  // v * mix(1, c, s); 1 * (1 - s) is exact
+}
+
+__global__ void __launch_bounds__(256) k_present(const __half *__restrict__ macro16, const __half *__restrict__ curl16, int nx,
+                                                 int ny, int W, int H, int row0, int rows, float4 *__restrict__ out) {
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= W || r >= rows) return;
+    const int py = row0 + r;
+    const float u = fdiv(fadd((float)px, 0.5f), (float)W), v = fdiv(fadd((float)py, 0.5f), (float)H);
+    const BilinearTaps t = bilinear_taps(nx, ny, u, v);
+    // macro texel = (u.x, u.y, rho, 1): three channels are used; of the curl texel only x
+    const uint2 *m = reinterpret_cast<const uint2 *>(macro16);
+    auto unpack = [](uint2 q, float &a, float &b, float &c) {
+        const __half2 lo = *reinterpret_cast<const __half2 *>(&q.x), hi = *reinterpret_cast<const __half2 *>(&q.y);
+        a = __low2float(lo); b = __high2float(lo); c = __low2float(hi);
+    };
+    float ax, ay, az, bx, by, bz, cx, cy, cz, dx, dy, dz;
+    unpack(m[t.o00], ax, ay, az); unpack(m[t.o10], bx, by, bz); unpack(m[t.o01], cx, cy, cz); unpack(m[t.o11], dx, dy, dz);
+    const float ux = bilinear_mix(t, ax, bx, cx, dx), uy = bilinear_mix(t, ay, by, cy, dy), rho = bilinear_mix(t, az, bz, cz, dz);
+    const float curl = bilinear_mix(t, __half2float(curl16[4 * (size_t)t.o00]), __half2float(curl16[4 * (size_t)t.o10]),
+                                    __half2float(curl16[4 * (size_t)t.o01]), __half2float(curl16[4 * (size_t)t.o11]));
+    const float speed = fadd(fabsf(ux), fabsf(uy));
+    const float sat = fadd(0.6f, fmul(speed, 1.4f)), val = fadd(0.6f, fmul(rho, 0.33f));
+    float4 o;
+    o.x = hsv2rgb_channel(curl, 1.0f, sat, val);
+    o.y = hsv2rgb_channel(curl, fdiv(2.0f, 3.0f), sat, val);
+    o.z = hsv2rgb_channel(curl, fdiv(1.0f, 3.0f), sat, val);
+    o.w = rho;
+    out[(size_t)r * W + px] = o;
+}
+
 // present.wgsl:19-22,43-49 — the in-place fade of the canvas that the present pass performs
 __global__ void __launch_bounds__(256) k_canvas_fade(Pixel *canvas, size_t n, float fade_out_factor) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

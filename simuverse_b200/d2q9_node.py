@@ -252,6 +252,15 @@ class D2Q9Node:
         check(lib.lbm_read_curl(self._h, ptr(out)), self._h)
         return out
 
+    def read_present(self, row0=0, rows=None):
+        """Fragment outputs of the reference's ``render_node`` (fluid_simulator.rs:69-87, lbm/present.wgsl:21-46) for
+        canvas rows [row0, row0 + rows): (rows, canvas_w, 4) float32 (r, g, b, a = rho) from the newest macro field."""
+        w, h = self.field_uniform_data.canvas_size[0], self.field_uniform_data.canvas_size[1]
+        rows = h - row0 if rows is None else rows
+        out = np.empty((rows, w, 4), np.float32)
+        check(lib.lbm_read_present(self._h, row0, rows, ptr(out)), self._h)
+        return out
+
     def read_lattice_info(self):
         out = np.empty(self.rows * self.lattice[0], dtype=LATTICE_INFO_DTYPE)
         check(lib.lbm_read_lattice_info(self._h, ptr(out)), self._h)

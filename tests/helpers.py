@@ -14,10 +14,11 @@ def golden_cases():
 
 def wgsl_golden_cases():
     """Vectors made by executing the reference's own WGSL source (tests/golden/make_wgsl_golden.py)."""
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "wgsl_*.npz")) if "wgsl_default" not in p and "wgsl_curl" not in p)
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "wgsl_*.npz")) if "wgsl_default" not in p and "wgsl_curl" not in p and "wgsl_present" not in p)
 
 
 WGSL_CURL = os.path.join(GOLDEN_DIR, "wgsl_curl_64x48.npz")
+WGSL_PRESENT = os.path.join(GOLDEN_DIR, "wgsl_present_64x48.npz")
 
 
 WGSL_DEFAULT = os.path.join(GOLDEN_DIR, "wgsl_default_600x375_f2.npz")

@@ -90,6 +90,8 @@ def lib():
         L.orc_particle_grid.argtypes = [u32, u32, i32, C.POINTER(i32), C.POINTER(i32)]
         L.orc_init_trajectory_particles.argtypes = [u32, u32, i32, i32, f32, u64, vp]
         L.orc_curl_update.argtypes = [i32, i32, vp, vp]
+        L.orc_present.restype = None
+        L.orc_present.argtypes = [vp, vp, vp, i32, i32, vp]
         L.orc_total_mass.restype = C.c_double
         L.orc_total_mass.argtypes = [i32, i32, vp]
         _lib = L
@@ -182,6 +184,19 @@ def curl_update(nx, ny, macro_f16):
     out = np.zeros(4 * nx * ny, np.uint16)
     lib().orc_curl_update(nx, ny, ptr(macro_f16), ptr(out))
     return out.reshape(ny, nx, 4)
+
+
+def present(field, macro_f16, curl_f16, row0=0, rows=None):
+    """lbm/present.wgsl (colour present of the field) for canvas rows [row0, row0 + rows): (rows, W, 4) float32."""
+    nx, ny = field.lattice_size[0], field.lattice_size[1]
+    W, H = field.canvas_size[0], field.canvas_size[1]
+    rows = H - row0 if rows is None else rows
+    macro_f16 = np.ascontiguousarray(macro_f16, np.uint16).reshape(-1)
+    curl_f16 = np.ascontiguousarray(curl_f16, np.uint16).reshape(-1)
+    assert macro_f16.size == 4 * nx * ny and curl_f16.size == 4 * nx * ny and 0 <= row0 and row0 + rows <= H
+    out = np.zeros((rows, W, 4), np.float32)
+    lib().orc_present(C.byref(field), ptr(macro_f16), ptr(curl_f16), row0, rows, ptr(out))
+    return out
 
 
 def canvas_fade(field, pu, canvas):

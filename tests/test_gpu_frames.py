@@ -287,3 +287,36 @@ def test_curl_pass_matches_executed_wgsl_and_oracle(orc):
         sim.step(60)
         np.testing.assert_array_equal(a.read_curl_tex().view(np.uint16), orc.curl_update(nx, ny, sim.macro_f16))
         a.close()
+
+
+def test_present_pass_matches_executed_wgsl_and_oracle(orc):
+    """lbm_read_present (lbm/present.wgsl:21-46, the fragment shader of the reference's `render_node`): fragment outputs
+    bit-equal to the executed shader text (golden, two target sizes) and to the oracle on larger fields, whole targets
+    and row windows, from the per-step texture (sweeps) and from the on-demand field."""
+    from helpers import WGSL_CURL, WGSL_PRESENT
+
+    g = np.load(WGSL_PRESENT)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    c100 = np.load(WGSL_CURL.replace("wgsl_curl_64x48", "wgsl_channel100_64x48_s100"))
+    for tag in "ab":
+        canvas = tuple(int(v) for v in g[f"canvas_{tag}"])
+        for flags in (sb.FLAG_MACRO_EVERY_STEP, 0):
+            a = sb.D2Q9Node(canvas, setting(W.CUSTOM), lattice=(nx, ny), lattice_info=c100["info"], flags=flags)
+            a.step_n(100)
+            assert_bits_equal(a.read_present(), g[f"rgba_{tag}"], f"target {canvas}, flags {flags}")
+            assert_bits_equal(a.read_present(5, 9), g[f"rgba_{tag}"][5:14], "row window")
+            a.close()
+    for nx, ny, preset, canvas in [(600, 375, W.POISEUILLE, (1200, 750)), (131, 77, W.LID_DRIVEN_CAVITY, (1000, 333))]:
+        info = orc.init_lattice_material(nx, ny, preset)
+        a = sb.D2Q9Node(canvas, setting(preset), lattice=(nx, ny), lattice_info=info, flags=sb.FLAG_MACRO_EVERY_STEP)
+        sim = oracle_for(orc, nx, ny, preset, info)
+        a.step_n(60)
+        sim.step(60)
+        field = orc.field_uniform_new(nx, ny, 2, *canvas)
+        want = orc.present(field, sim.macro_f16, orc.curl_update(nx, ny, sim.macro_f16))
+        got = a.read_present()
+        assert_bits_equal(got, want, f"{nx}x{ny} -> {canvas}")
+        assert len(np.unique(got.reshape(-1, 4), axis=0)) > 1000  # a real picture, not a constant
+        with pytest.raises(sb.LbmError):
+            a.read_present(canvas[1] - 2, 3)
+        a.close()

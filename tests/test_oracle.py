@@ -342,3 +342,46 @@ def test_curl_pass_matches_executed_reference_wgsl(orc):
     tex[..., 1] = 1.0
     c = orc.curl_update(7, 5, tex.view(np.uint16)).view(np.float16)[..., 0]
     assert (c[:, :6] == 0.5).all() and (c[:, 6] == -3.0).all()
+
+
+def test_present_pass_matches_executed_reference_wgsl(orc):
+    """oracle.present against the fragment outputs produced by executing lbm/present.wgsl per pixel (tests/golden/
+    make_wgsl_golden_present.py) on two target sizes, bit for bit; plus hand-checked cases of the hsv2rgb / filter
+    arithmetic, and a live re-run of a few rows when the reference tree is present."""
+    from helpers import WGSL_CURL, WGSL_PRESENT
+
+    g, c = np.load(WGSL_PRESENT), np.load(WGSL_CURL)
+    nx, ny = int(g["nx"]), int(g["ny"])
+    for tag in "ab":
+        W, H = (int(v) for v in g[f"canvas_{tag}"])
+        field = orc.field_uniform_new(nx, ny, 2, W, H)
+        got = orc.present(field, c["macro_f16"], c["curl_f16"])
+        assert_bits_equal(got, g[f"rgba_{tag}"], f"present target {W}x{H}")
+        # a window of rows equals the same rows of the whole target
+        assert_bits_equal(orc.present(field, c["macro_f16"], c["curl_f16"], 7, 5), g[f"rgba_{tag}"][7:12], "row window")
+    # uniform textures: every filter weight sums to the texel value (weights (1-f)(1-g)+... are exact for f = g = 0.5 at
+    # an integer ratio of 2), curl.x = 0.5 -> hue 0.5: p = |fract(0.5 + K) * 6 - 3| = (0, 1, 1) + rounding of 2/3, 1/3
+    tex = np.zeros((4, 4, 4), np.float16)
+    tex[..., 2] = 1.0  # rho = 1, u = 0
+    curl = np.zeros((4, 4, 4), np.float16)
+    curl[..., 0] = 0.5
+    field = orc.field_uniform_new(4, 4, 2, 8, 8)
+    out = orc.present(field, tex.view(np.uint16), curl.view(np.uint16))
+    f = np.float32
+    v = f(0.6) + f(1.0) * f(0.33)
+    s = f(0.6)
+    want_r = v * (f(1.0) * (f(1.0) - s) + f(0.0) * s)   # c = clamp(|fract(1.5) * 6 - 3| - 1) = clamp(-1) = 0
+    assert (out[..., 3] == 1.0).all() and (out[..., 0] == want_r).all()
+    assert np.all(out[..., 1] > out[..., 0]) and np.all(out[..., 2] > out[..., 0])  # cyan: g, b at full value
+    from wgsl_ref import harness as H_
+
+    if H_.available():
+        from simuverse_b200.d2q9_node import lbm_uniform_new
+
+        ch = np.load(WGSL_PRESENT.replace("wgsl_present_64x48", "wgsl_channel100_64x48_s100"))
+        W, H = (int(v) for v in g["canvas_b"])
+        sim = H_.WgslLbm(nx, ny, ch["info"], lbm_uniform_new(0.56, 0, nx * ny), canvas=(W, H))
+        sim.macro[...] = c["macro_f16"].view(np.float16).reshape(ny, nx, 4)
+        rows = [0, 50, H - 1]
+        live = sim.present(c["curl_f16"].view(np.float16).reshape(ny, nx, 4), rows=rows)
+        assert_bits_equal(live[rows], g["rgba_b"][rows], "live re-run of lbm/present.wgsl")

@@ -42,10 +42,11 @@ class WgslLbm:
     # ---- resource binding
     def _bind_common(self, ns):
         u = self.u
-        ns["fluid"] = ns["LbmUniform"](
-            F(u.tau), F(u.omega), int(u.fluid_ty), int(u.soa_offset),
-            [rt.Vec([F(c) for c in u.e_w_max[i]]) for i in range(9)],
-            [rt.Vec([int(c) for c in u.inversed_direction[i]]) for i in range(9)])
+        if "LbmUniform" in ns:
+            ns["fluid"] = ns["LbmUniform"](
+                F(u.tau), F(u.omega), int(u.fluid_ty), int(u.soa_offset),
+                [rt.Vec([F(c) for c in u.e_w_max[i]]) for i in range(9)],
+                [rt.Vec([int(c) for c in u.inversed_direction[i]]) for i in range(9)])
         ns["field"] = ns["FieldUniform"](
             rt.Vec([self.nx, self.ny]), rt.Vec([F(self.lps), F(self.lps)]), rt.Vec(list(self.canvas_size)),
             rt.Vec([F(0), F(0)]), rt.Vec([F(0), F(0)]), 1)
@@ -95,6 +96,36 @@ class WgslLbm:
             for gx in range(-(-self.nx // 64) * 64):
                 main(rt.Vec([gx, gy, 0]))
         return curl
+
+    # ---- colour present of the field (lbm/present.wgsl; `render_node`, built by the reference but its draw call is
+    # commented out: fluid_simulator.rs:69-87,243-244)
+    def present(self, curl, canvas=None, rows=None):
+        """Runs the fragment shader lbm/present.wgsl once per pixel of a canvas_size render target and returns the
+        (H, W, 4) float32 fragment outputs (before the surface-format conversion).  Fragment inputs as the rasteriser
+        defines them for the bufferless full-screen triangle (bufferless.vs.wgsl): position = pixel centre, uv =
+        position.xy / target size (f32 division).  `curl`: the (ny, nx, 4) f16 texture of curl_update()."""
+        if "present" not in self.mods:
+            self.mods["present"] = _load("lbm/present.wgsl")
+            self._bind_common(self.mods["present"])
+        ns = self.mods["present"]
+        W, H = self.canvas_size
+        if canvas is None:
+            canvas = np.zeros(W * H, np.dtype([("alpha", "<f4"), ("velocity_x", "<f4"), ("velocity_y", "<f4")]))
+        ns["particle_uniform"] = ns["ParticleUniform"]()
+        ns["canvas"] = rt.StructArray(canvas, ns["Pixel"],
+                                      lambda cls, rec: cls(F(rec["alpha"]), F(rec["velocity_x"]), F(rec["velocity_y"])),
+                                      None)
+        ns["macro_info"] = rt.Texture16F(self.macro)
+        ns["cur_info"] = rt.Texture16F(curl)
+        ns["tex_sampler"] = rt.BilinearClampSampler()
+        out = np.zeros((H, W, 4), np.float32)
+        main, VO = ns["fs_main"], ns["VertexOutput"]
+        for py in (range(H) if rows is None else rows):
+            for px in range(W):
+                pos = rt.Vec([F(px + 0.5), F(py + 0.5), F(0.1), F(1.0)])
+                uv = rt.Vec([F(pos.v[0] / F(W)), F(pos.v[1] / F(H))])
+                out[py, px, :] = main(VO(uv, pos)).v
+        return out
 
     # ---- particles (particle_update.wgsl)
     def bind_particles(self, pu, particles, canvas):

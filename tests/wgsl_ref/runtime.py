@@ -216,3 +216,53 @@ def textureLoad(tex, uv, level):
         # lbm/curl_update.wgsl gets here (its `min(.., lattice_size)` clamp is one past the last texel).
         return Vec([F(0.0)] * 4)
     return Vec([F(c) for c in tex.arr[y, x, :].astype(np.float32)])
+
+
+# ---------------------------------------------------------------- builtins of the render shaders (lbm/present.wgsl)
+def fract(x): return _map(lambda a: F(a - F(np.floor(a))), x)   # WGSL: e - floor(e)
+
+
+def mix(a, b, t):
+    """WGSL linear blend, the spec's own expression e1 * (1 - e3) + e2 * e3, one f32 rounding per operation."""
+    return _map(lambda x, y, w: F(F(x * F(F(1.0) - w)) + F(y * w)), a, b, t)
+
+
+def atan2(y, x): return _map(lambda p, q: F(np.arctan2(F(p), F(q))), y, x)
+
+
+class BilinearClampSampler:
+    """util/load_texture.rs:229-243 `bilinear_sampler`: ClampToEdge, linear mag / min filter (one mip level)."""
+
+
+def textureSample(tex, sampler, uv):
+    """textureSample of a 2D rgba16float texture through `bilinear_sampler`.  WebGPU (like Vulkan / Metal / D3D) leaves
+    the precision of the filter weights to the hardware (fixed point, >= 4 fractional bits); this restatement — and the
+    oracle and the CUDA pass pinned on it — evaluate the spec's formula in f32, one rounding per operation:
+        c = uv * size - 0.5;  i0 = floor(c);  f = c - i0;  taps clamped to the edge;
+        (1-fx)(1-fy) t00 + fx(1-fy) t10 + (1-fx) fy t01 + fx fy t11, summed in that order."""
+    assert isinstance(sampler, BilinearClampSampler)
+    ny, nx = tex.arr.shape[:2]
+    cx = F(F(F(uv.v[0]) * F(nx)) - F(0.5))
+    cy = F(F(F(uv.v[1]) * F(ny)) - F(0.5))
+    fx0, fy0 = F(np.floor(cx)), F(np.floor(cy))
+    fx, fy = F(cx - fx0), F(cy - fy0)
+    import builtins
+    x0 = builtins.min(builtins.max(int(fx0), 0), nx - 1)
+    x1 = builtins.min(builtins.max(int(fx0) + 1, 0), nx - 1)
+    y0 = builtins.min(builtins.max(int(fy0), 0), ny - 1)
+    y1 = builtins.min(builtins.max(int(fy0) + 1, 0), ny - 1)
+    gx, gy = F(F(1.0) - fx), F(F(1.0) - fy)
+    w00, w10, w01, w11 = F(gx * gy), F(fx * gy), F(gx * fy), F(fx * fy)
+
+    def t(y, x):
+        return [F(c) for c in tex.arr[y, x, :].astype(np.float32)]
+
+    t00, t10, t01, t11 = t(y0, x0), t(y0, x1), t(y1, x0), t(y1, x1)
+    out = []
+    for k in range(4):
+        s = F(w00 * t00[k])
+        s = F(s + F(w10 * t10[k]))
+        s = F(s + F(w01 * t01[k]))
+        s = F(s + F(w11 * t11[k]))
+        out.append(s)
+    return Vec(out)

@@ -310,7 +310,13 @@ class Parser:
 
 SCALAR_CONV = {"f32": "_rt.f32", "i32": "_rt.i32", "u32": "_rt.u32", "bool": "bool"}
 BUILTINS = {"dot", "clamp", "floor", "abs", "min", "max", "length", "smoothstep", "textureLoad", "textureStore", "sqrt",
-            "atan2", "cos", "sin", "ceil", "round", "select", "fract"}
+            "atan2", "cos", "sin", "ceil", "round", "select", "fract", "mix", "textureSample"}
+PY_KEYWORDS = {"in", "is", "from", "pass", "def", "class", "lambda", "with", "as", "not", "and", "or", "global", "del"}
+
+
+def pyname(n):
+    """WGSL identifiers that are Python keywords (`in: VertexOutput` of the fragment shaders) get a trailing underscore."""
+    return n + "_" if n in PY_KEYWORDS else n
 
 
 class Emitter:
@@ -362,7 +368,7 @@ class Emitter:
 
     def function(self, d):
         _, name, params, ret, body, attrs = d
-        self.lines.append(f"def {name}({', '.join(p for p, _ in params)}):")
+        self.lines.append(f"def {name}({', '.join(pyname(p) for p, _ in params)}):")
         n0 = len(self.lines)
         self.block(body, 1)
         if len(self.lines) == n0:
@@ -380,9 +386,9 @@ class Emitter:
             elif k == "var":
                 _, name, ty, init = s
                 if init is None:
-                    self.lines.append(f"{pad}{name} = {self.zero(ty)}")
+                    self.lines.append(f"{pad}{pyname(name)} = {self.zero(ty)}")
                 else:
-                    self.lines.append(f"{pad}{name} = _rt.copy({self.conv(ty, self.ex(init))})")
+                    self.lines.append(f"{pad}{pyname(name)} = _rt.copy({self.conv(ty, self.ex(init))})")
             elif k == "assign":
                 self.lines.append(f"{pad}{self.lvalue(s[1])} = _rt.copy({self.ex(s[2])})")
             elif k == "expr":
@@ -416,7 +422,7 @@ class Emitter:
 
     def lvalue(self, e):
         if e[0] == "name":
-            return e[1]
+            return pyname(e[1])
         if e[0] == "member":
             return f"{self.ex(e[1])}.{e[2]}"
         if e[0] == "index":
@@ -435,7 +441,7 @@ class Emitter:
         if k == "bool":
             return "True" if e[1] else "False"
         if k == "name":
-            return e[1]
+            return pyname(e[1])
         if k == "paren":
             return f"({self.ex(e[1])})"
         if k == "neg":
