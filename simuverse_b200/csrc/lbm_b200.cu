@@ -1492,7 +1492,7 @@ extern "C" int lbm_total_mass(LbmSim *s, int32_t which, double *out) {
         k_sum_dense<<<148 * 4, 256, 0, s->stream>>>(s->scratch_dense, (size_t)9 * s->P.h * s->P.nx, s->d_mass);
         rc = check_launch(s, "k_sum_dense");
     } else {
-        k_mass<<<148 * 4, 256, 0, s->stream>>>(s->P, which, s->d_mass);
+        k_mass<<<148 * 8, 256, 0, s->stream>>>(s->P, which, s->d_mass);
         rc = check_launch(s, "k_mass");
     }
     if (rc) return rc;
