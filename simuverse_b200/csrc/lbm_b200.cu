@@ -130,8 +130,15 @@ struct LbmSim {
     // frames with tracer particles as sweeps: the texture update 1 of a sweep stores into, and graphs of TWO frames
     // (sweep, particles(t+1), particles(t+2)) x 2 — an even number of sweeps leaves the buffer pointers unchanged
     __half *macro_mid = nullptr;
-    cudaGraphExec_t graph_pframes[2] = {nullptr, nullptr}; // [flip]
-    uint64_t graph_pframes_kernels[2] = {0, 0};
+    // Frames with tracer particles, overlapped: the two particle passes of frame f only read the textures sweep f stored
+    // and sweep f+1 only reads the distributions, so inside a captured run of frames the passes run on a second stream
+    // beside the next sweep.  Two texture sets alternate (set 0 = the handle's own macro_mid / macro16, set 1 = these).
+    __half *macro_mid2 = nullptr, *macro_alt = nullptr;
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_sweep = nullptr, ev_part[2] = {nullptr, nullptr};
+    bool overlap_particles = true;         // LBM_PARTICLE_OVERLAP=0: everything on one stream (A/B runs)
+    cudaGraphExec_t graph_pframes[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + (8-frame run ? 1 : 0)]
+    uint64_t graph_pframes_kernels[4] = {0, 0, 0, 0};
     uint64_t fused_sweeps = 0;
     std::string err;
 };
@@ -309,10 +316,10 @@ void invalidate_graphs(LbmSim *s) {
 bool graphs_enabled(const LbmSim *s) { return !(s->d.flags & LBM_FLAG_NO_GRAPH); }
 
 // tex: the macro texture to sample (nullptr = the one the latest update wrote)
-int launch_particles(LbmSim *s, const __half *tex = nullptr) {
+int launch_particles(LbmSim *s, const __half *tex = nullptr, cudaStream_t stream = nullptr) {
     SlabParams Q = s->P;
     if (tex) Q.macro16 = const_cast<__half *>(tex);
-    cudaError_t e = launch_particle_update(Q, s->field, s->pu, s->particles, s->canvas, s->stream);
+    cudaError_t e = launch_particle_update(Q, s->field, s->pu, s->particles, s->canvas, stream ? stream : s->stream);
     if (e != cudaSuccess) return fail(s, LBM_ERR_CUDA, "launch of k_particle_update failed: %s", cudaGetErrorString(e));
     s->launches++;
     return LBM_OK;
@@ -668,6 +675,11 @@ extern "C" void lbm_destroy(LbmSim *s) {
     cudaFree(s->macro_buf[0] ? s->macro_buf[0] : s->P.macro16);
     cudaFree(s->macro_buf[1]);
     cudaFree(s->macro_mid);
+    cudaFree(s->macro_mid2);
+    cudaFree(s->macro_alt);
+    if (s->side_stream) { cudaStreamSynchronize(s->side_stream); cudaStreamDestroy(s->side_stream); }
+    if (s->ev_sweep) cudaEventDestroy(s->ev_sweep);
+    for (auto e : s->ev_part) if (e) cudaEventDestroy(e);
     cudaFree(s->prev_spare_alloc);
     for (auto p : s->stage) if (p) cudaFreeHost(p);
     for (auto e : s->stage_ev) if (e) cudaEventDestroy(e);
@@ -794,6 +806,7 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
     lbm_field_uniform_new(d.nx, d.ny, (uint32_t)d.lattice_pixel_size, s->canvas_w, s->canvas_h, &s->field);
 
     if (const char *e = getenv("LBM_FUSE_MASKED")) s->use_masked = atoi(e) != 0; // A/B runs, tests
+    if (const char *e = getenv("LBM_PARTICLE_OVERLAP")) s->overlap_particles = atoi(e) != 0;
     s->sync.flags = reinterpret_cast<unsigned int *>(s->arena + s->flag_off);
     s->sync.world = d.world;
     {
@@ -1156,21 +1169,61 @@ extern "C" int lbm_compute_frames(LbmSim *s, int32_t n_frames) {
         };
         int left = n_frames;
         const bool graphs = graphs_enabled(s) && n_frames >= 4;
-        if (graphs && !s->graph_pframes[s->flip]) {
-            rc = capture_graph(s, &s->graph_pframes[s->flip], &s->graph_pframes_kernels[s->flip], [&]() {
-                int r = pframe();
-                return r == LBM_OK ? pframe() : r;
+        // A captured run of F frames (F even: the buffer pointers and the texture set end where they started).  Frame f
+        // stores its textures into set (f + 1) & 1, so the last frame's are the handle's own; the particle passes of frame
+        // f wait for sweep f, run one after the other on the side stream (the order among the passes is the reference's),
+        // and sweep f + 2 — the next writer of their texture set — waits for them.
+        const int F = n_frames >= 8 ? 8 : 4;
+        const int gkey = s->flip * 2 + (F == 8 ? 1 : 0);
+        if (graphs && !s->graph_pframes[gkey]) {
+            const bool overlap = s->overlap_particles;
+            if (overlap && !s->side_stream) {
+                const size_t bytes = sizeof(__half) * 4 * (size_t)s->P.h * s->P.nx;
+                CU(cudaMalloc(&s->macro_mid2, bytes));
+                CU(cudaMalloc(&s->macro_alt, bytes));
+                CU(cudaMemsetAsync(s->macro_mid2, 0, bytes, s->stream));
+                CU(cudaMemsetAsync(s->macro_alt, 0, bytes, s->stream));
+                CU(cudaEventCreateWithFlags(&s->ev_sweep, cudaEventDisableTiming));
+                for (auto &e : s->ev_part) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                CU(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+            }
+            rc = capture_graph(s, &s->graph_pframes[gkey], &s->graph_pframes_kernels[gkey], [&]() {
+                int r = LBM_OK;
+                if (!overlap) {
+                    for (int f = 0; f < F && r == LBM_OK; f++) r = pframe();
+                    return r;
+                }
+                __half *const mid[2] = {s->macro_mid, s->macro_mid2}, *const end[2] = {s->P.macro16, s->macro_alt};
+                cudaError_t e = cudaSuccess;
+                for (int f = 0; f < F && r == LBM_OK && e == cudaSuccess; f++) {
+                    const int set = (f + 1) & 1;
+                    if (f >= 2) e = cudaStreamWaitEvent(s->stream, s->ev_part[set], 0); // passes of frame f - 2 read this set
+                    s->P.macro16 = end[set];
+                    s->macro_mid = mid[set];
+                    r = launch_pair(s, 0, true);
+                    if (e == cudaSuccess) e = cudaEventRecord(s->ev_sweep, s->stream);
+                    if (e == cudaSuccess) e = cudaStreamWaitEvent(s->side_stream, s->ev_sweep, 0);
+                    if (r == LBM_OK && e == cudaSuccess) r = launch_particles(s, mid[set], s->side_stream);
+                    if (r == LBM_OK && e == cudaSuccess) r = launch_particles(s, end[set], s->side_stream);
+                    if (e == cudaSuccess) e = cudaEventRecord(s->ev_part[set], s->side_stream);
+                }
+                s->P.macro16 = end[0];
+                s->macro_mid = mid[0];
+                // join: the passes of the last frame (set 0) are the last work of the side stream
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(s->stream, s->ev_part[0], 0);
+                if (r == LBM_OK && e != cudaSuccess) r = fail(s, LBM_ERR_CUDA, "capturing overlapped particle frames failed: %s", cudaGetErrorString(e));
+                return r;
             });
             if (rc) return rc;
         }
         CU(cudaEventRecord(s->ev0, s->stream));
         if (graphs) {
-            for (; left >= 2; left -= 2) {
-                CU(cudaGraphLaunch(s->graph_pframes[s->flip], s->stream));
-                s->launches += s->graph_pframes_kernels[s->flip];
-                s->steps_since_reset += 4;
-                s->macro_writes += 4;
-                s->fused_sweeps += 2;
+            for (; left >= F; left -= F) {
+                CU(cudaGraphLaunch(s->graph_pframes[gkey], s->stream));
+                s->launches += s->graph_pframes_kernels[gkey];
+                s->steps_since_reset += 2 * F;
+                s->macro_writes += 2 * F;
+                s->fused_sweeps += F;
                 s->prev_stale = true;
             }
         }

@@ -51,7 +51,9 @@ def test_particle_frames_on_sweeps_equal_single_update_frames(orc, nx, ny, solid
     fb, b, _ = fluid_sim(nx, ny, info, sb.FLAG_NO_FUSE)
     sim = oracle_for(orc, nx, ny, W.POISEUILLE, info)
     frames = 0
-    for k in (1, 2, 9, 12):        # single calls, and graph replays of two frames (k >= 4)
+    # single calls; captured runs of 4 (4 <= k < 8) and 8 frames, whose particle passes run on a side stream beside the
+    # next sweep (two alternating texture sets), plus the frames left over after the last run
+    for k in (1, 2, 5, 9, 12):
         fa.compute(k)
         fb.compute(k)
         frames += k
