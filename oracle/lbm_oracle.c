@@ -2,8 +2,8 @@
  * lbm_oracle.c — CPU restatement of the reference's D2Q9 LBM path (see lbm_oracle.h).
  *
  * TEST INFRASTRUCTURE ONLY — never linked into, loaded by, or called from the product.
- * Pinned to the reference's WGSL source executed by tests/wgsl_ref (see lbm_oracle.h); the Rust host
- * helpers restated here remain unpinned by execution.
+ * Pinned to the reference's WGSL source executed by tests/wgsl_ref and to its Rust host helpers
+ * executed by tests/rust_ref (see lbm_oracle.h).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math [-fopenmp]  (oracle/Makefile).
  * Every expression is written in the reference's source order so that, with FMA

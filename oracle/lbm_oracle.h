@@ -12,10 +12,12 @@
  * (after the reference's #include expansion) to Python and evaluates them with IEEE f32 scalars;
  * tests/golden/make_wgsl_golden.py commits the resulting vectors (tests/golden/wgsl_*.npz) and
  * tests/test_oracle.py requires this oracle to reproduce them bit for bit (distributions, macro
- * texture, LatticeInfo, particles, canvas).  Not pinned by execution: the Rust HOST helpers
- * (LbmUniform::new, init_lattice_material, add_obstacle, add_external_force, particle seeding),
- * which are restated from source and checked only against the derived known answers of
- * SURVEY.md §8c — "parity unpinned" still applies to those.
+ * texture, LatticeInfo, particles, canvas).  The Rust HOST helpers (LbmUniform::new,
+ * init_lattice_material, add_obstacle, add_external_force, the click / drag guards, update_uniforms,
+ * the tracer grid) are pinned the same way: tests/rust_ref executes their bodies cut out of the
+ * reference's .rs files, tests/golden/make_rust_golden.py commits masks, uniform bytes, a click
+ * sequence and a drag, and tests/test_rust_ref.py requires this oracle to reproduce every byte.
+ * Not pinned: the tracer seeding (the reference draws from an unseeded rand::rng()).
  *
  * This file restates the reference's in-tree arithmetic — the WGSL shaders and the Rust host
  * functions cited per function — in plain C, f32, round-to-nearest, no FMA contraction

@@ -9,7 +9,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def golden_cases():
     """Vectors made by the independent numpy restatement (tests/golden/make_golden.py)."""
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith("wgsl_"))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")) if not os.path.basename(p).startswith(("wgsl_", "rust_")))
 
 
 def wgsl_golden_cases():

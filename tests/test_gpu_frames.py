@@ -322,3 +322,37 @@ def test_present_pass_matches_executed_wgsl_and_oracle(orc):
         with pytest.raises(sb.LbmError):
             a.read_present(canvas[1] - 2, 3)
         a.close()
+
+
+def test_clicks_and_drag_of_the_executed_rust_golden_through_the_device(orc):
+    """The click / drag sequence of tests/golden/rust_host_helpers.npz (produced by executing the reference's Rust text)
+    driven through FluidSimulator.on_click / touch_move on a real handle: the device's info buffer ends up with exactly
+    the bytes the reference's write_buffer calls would have left, and the lattice then steps like the oracle's."""
+    import os
+
+    from helpers import GOLDEN_DIR
+
+    g = np.load(os.path.join(GOLDEN_DIR, "rust_host_helpers.npz"))
+    nx, ny, lps = (int(v) for v in g["lattice"])
+    fs = sb.FluidSimulator((nx * lps, ny * lps), setting(W.POISEUILLE), particles=False, lattice=(nx, ny),
+                           lattice_info=g["mask_0"])
+    node = fs.fluid_compute_node
+    want = g["mask_0"].copy()
+    for pos, wrote in zip(g["clicks"], g["click_wrote"]):
+        assert fs.on_click((float(pos[0]), float(pos[1]))) == bool(wrote)
+    for off, patch in zip(g["click_offsets"], g["click_patches"]):
+        want[int(off) // 16:int(off) // 16 + patch.size] = patch
+    fs.touch_begin()
+    for pos, count in zip(g["drag"], g["drag_write_counts"]):
+        assert fs.touch_move((float(pos[0]), float(pos[1]))) == int(count)
+    for off, cell in zip(g["drag_offsets"], g["drag_cells"]):
+        want[int(off) // 16] = cell
+    assert node.read_lattice_info().tobytes() == want.tobytes()
+    sim = oracle_for(orc, nx, ny, W.POISEUILLE, g["mask_0"])
+    sim.write_lattice_info(0, want)
+    node.step_n(100)   # the armed force cells (block_iter 90) count down and retire on the way
+    sim.step(100)
+    for which in (0, 1):
+        assert_bits_equal(node.read_distributions(which), sim.distributions(which), f"buf{which} after the drag")
+    assert node.read_lattice_info().tobytes() == sim.info.tobytes()
+    node.close()
