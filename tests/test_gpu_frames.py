@@ -352,7 +352,9 @@ def test_clicks_and_drag_of_the_executed_rust_golden_through_the_device(orc):
     sim.write_lattice_info(0, want)
     node.step_n(100)   # the armed force cells (block_iter 90) count down and retire on the way
     sim.step(100)
+    # (slots of the painted discs that only another solid would read keep leftovers that are racy in the reference itself)
+    live = live_slots(want["material"].reshape(ny, nx))
     for which in (0, 1):
-        assert_bits_equal(node.read_distributions(which), sim.distributions(which), f"buf{which} after the drag")
+        assert_bits_equal(node.read_distributions(which)[live], sim.distributions(which)[live], f"buf{which} after the drag")
     assert node.read_lattice_info().tobytes() == sim.info.tobytes()
     node.close()
