@@ -127,8 +127,8 @@ struct LbmSim {
     int flip = 0;                          // parity of the buffer-pointer exchanges done by two-update sweeps
     cudaGraphExec_t graph_pairs[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + swap]: kGraphSteps / 2 sweeps
     uint64_t graph_pairs_kernels[4] = {0, 0, 0, 0};
-    // frames with tracer particles as sweeps: the texture update 1 of a sweep stores into, and graphs of TWO frames
-    // (sweep, particles(t+1), particles(t+2)) x 2 — an even number of sweeps leaves the buffer pointers unchanged
+    // frames with tracer particles as sweeps: the texture update 1 of a sweep stores into; graphs of 4 / 8 frames
+    // (sweep, particles(t+1), particles(t+2)) — an even number of sweeps leaves the buffer pointers unchanged
     __half *macro_mid = nullptr;
     // Frames with tracer particles, overlapped: the two particle passes of frame f only read the textures sweep f stored
     // and sweep f+1 only reads the distributions, so inside a captured run of frames the passes run on a second stream
@@ -137,6 +137,7 @@ struct LbmSim {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_sweep = nullptr, ev_part[2] = {nullptr, nullptr};
     bool overlap_particles = true;         // LBM_PARTICLE_OVERLAP=0: everything on one stream (A/B runs)
+    bool pdl = false;                      // LBM_PDL=1: sweeps are launched with programmatic stream serialization
     cudaGraphExec_t graph_pframes[4] = {nullptr, nullptr, nullptr, nullptr}; // [flip * 2 + (8-frame run ? 1 : 0)]
     uint64_t graph_pframes_kernels[4] = {0, 0, 0, 0};
     uint64_t fused_sweeps = 0;
@@ -495,12 +496,30 @@ int fuse_eligible(LbmSim *s, bool *ok) {
     return LBM_OK;
 }
 
+// Programmatic dependent launch (LbmSim::pdl): the sweep kernel signals at its very start that its successor in the stream
+// may be launched, and waits — first thing, before it touches memory — for its predecessor to have completed
+// (griddepcontrol in k_frame2).  The next sweep's CTAs are then already resident when the last CTAs of this one retire:
+// the launch latency between dependent sweeps disappears (it is what a frame of a small, L2-resident lattice consists of).
+template <typename K>
+void launch_sweep_kernel(const LbmSim *s, K kernel, unsigned int grid, int first) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kFuseThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = s->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, s->P, s->sync, first, s->fuse);
+}
+
 template <bool SYMW, bool SLABS, bool MASKED>
 void launch_frame2m(const LbmSim *s, unsigned int grid, int first, int macro) {
-    const FuseGeom &g = s->fuse;
-    if (macro == 2) k_frame2<SYMW, SLABS, 2, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-    else if (macro == 1) k_frame2<SYMW, SLABS, 1, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
-    else k_frame2<SYMW, SLABS, 0, MASKED><<<grid, kFuseThreads, 0, s->stream>>>(s->P, s->sync, first, g);
+    if (macro == 2) launch_sweep_kernel(s, k_frame2<SYMW, SLABS, 2, MASKED>, grid, first);
+    else if (macro == 1) launch_sweep_kernel(s, k_frame2<SYMW, SLABS, 1, MASKED>, grid, first);
+    else launch_sweep_kernel(s, k_frame2<SYMW, SLABS, 0, MASKED>, grid, first);
 }
 
 template <bool SYMW, bool SLABS>
@@ -807,6 +826,7 @@ static int create_impl(LbmSim *s, const LbmDesc *desc) {
 
     if (const char *e = getenv("LBM_FUSE_MASKED")) s->use_masked = atoi(e) != 0; // A/B runs, tests
     if (const char *e = getenv("LBM_PARTICLE_OVERLAP")) s->overlap_particles = atoi(e) != 0;
+    if (const char *e = getenv("LBM_PDL")) s->pdl = atoi(e) != 0;
     s->sync.flags = reinterpret_cast<unsigned int *>(s->arena + s->flag_off);
     s->sync.world = d.world;
     {

@@ -29,6 +29,19 @@ def test_masks_match_executed_rust(orc):
         assert sb.init_lattice_material(int(nx), int(ny), int(ty)).tobytes() == want, f"product mask {nx}x{ny} ty {ty}"
 
 
+def test_mask_of_baseline_config_2_matches_executed_rust(orc):
+    """4096 x 4096 Poiseuille mask (BASELINE configs[1]): CRC32 of the i32-LE material array, histogram and the inlet's
+    vx as produced by executing init_lattice_material's text over all 16.7 M cells (make_rust_golden.py --crc4096)."""
+    import zlib
+
+    for gen in (orc.init_lattice_material, sb.init_lattice_material):
+        m = gen(4096, 4096, W.POISEUILLE)
+        assert zlib.crc32(m["material"].astype("<i4").tobytes()) == int(G["mask4096_crc"]) == 0x63A17811
+        np.testing.assert_array_equal(np.bincount(m["material"], minlength=8), G["mask4096_hist"])
+        assert float(m["vx"].astype(np.float64).sum()) == float(G["mask4096_vx_sum"])
+        assert (m["block_iter"] == -1).all() and (m["vy"] == 0).all()
+
+
 def test_uniforms_match_executed_rust(orc):
     """LbmUniform::new (fluid/mod.rs:32-55) and update_uniforms (fluid_simulator.rs:175-193)"""
     want = G["uniform_bytes"].tobytes()
