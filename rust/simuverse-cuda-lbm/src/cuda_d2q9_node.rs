@@ -141,15 +141,15 @@ impl CudaD2Q9Node {
         let (first_row, last_row) = (y - radius, y + radius); // rows first_row .. last_row (exclusive)
         let width = self.lattice.width;
         let centre = glam::Vec2::new(x as f32 + 0.5, y as f32 + 0.5);
-        let span = (width * first_row) as usize..(width * last_row) as usize;
-        for (k, cell) in self.lattice_info_data[span.clone()].iter_mut().enumerate() {
-            let (cx, cy) = (k as u32 % width, first_row + k as u32 / width);
+        let (first, last) = ((width * first_row) as usize, (width * last_row) as usize);
+        for index in first..last {
+            let (cx, cy) = (index as u32 % width, index as u32 / width);
             let from_centre = glam::Vec2::new(cx as f32 + 0.5, cy as f32 + 0.5) - centre;
             if is_sd_sphere(&from_centre, OBSTACLE_RADIUS) {
-                *cell = disc;
+                self.lattice_info_data[index] = disc;
             }
         }
-        self.upload_info((width * first_row) as u64 * 16, &self.lattice_info_data[span])
+        self.upload_info(first as u64 * 16, &self.lattice_info_data[first..last])
     }
 
     /// `reset_lattice_info` (d2q9_node.rs:247-261): the Poiseuille preset forgets painted obstacles, then init.

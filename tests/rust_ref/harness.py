@@ -171,3 +171,81 @@ def particle_grid(canvas_w, canvas_h, count):
                                                                F(60.0))
     assert len(particles) == namespace()["MAX_PARTICLE_COUNT"]
     return (size.width, size.height), tuple(groups)
+
+
+# ---------------------------------------------------------------- the repo's own Rust shim, executed the same way
+SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "rust",
+                    "simuverse-cuda-lbm", "src")
+_shim_ns = None
+
+
+def shim_namespace():
+    """rust/simuverse-cuda-lbm/src/{cuda_d2q9_node,cuda_fluid_simulator}.rs cannot be compiled in this image either.  Their
+    host-logic bodies are transpiled like the reference's and run on top of the reference's own items they import
+    (`OBSTACLE_RADIUS`, `is_sd_sphere`, `LbmUniform::new`, `LatticeType`), against a stand-in for the FFI calls."""
+    global _shim_ns
+    if _shim_ns is not None:
+        return _shim_ns
+    ns = dict(namespace())
+    read = lambda f: open(os.path.join(SHIM, f), encoding="utf-8").read()  # noqa: E731
+    node, sim = read("cuda_d2q9_node.rs"), read("cuda_fluid_simulator.rs")
+    code = ["def Ok(v=None):\n    return v\n"]
+    for fn in ("add_obstacle", "add_external_force"):
+        code.append(rust2py.transpile_fn(rust2py.extract_fn(node, fn)))
+    for fn in ("on_click", "touch_begin", "touch_move", "update_uniforms"):
+        code.append(rust2py.transpile_fn(rust2py.extract_fn(sim, fn)))
+    src = "\n".join(code)
+    exec(compile(src, "<rust/simuverse-cuda-lbm host logic>", "exec"), ns)
+    ns["__source__"] = src
+    _shim_ns = ns
+    return ns
+
+
+class ShimNode:
+    """CudaD2Q9Node with the FFI behind `upload_info` / `write_uniform` replaced by recorders."""
+
+    def __init__(self, nx, ny, lattice_pixel_size, ty, info):
+        self.lattice = types.SimpleNamespace(width=nx, height=ny, depth_or_array_layers=1)
+        self.lattice_pixel_size = lattice_pixel_size
+        self.animation_ty = animation(ty)
+        self.lattice_info_data = array_to_info(info)
+        self.writes = []
+
+    def upload_info(self, byte_offset, cells):
+        self.writes.append(("info_buf", int(byte_offset), info_to_array(list(cells)).tobytes()))
+
+    def write_uniform(self, uniform):
+        self.writes.append(("lbm_uniform_buf", 0, uniform_bytes(uniform)))
+
+    def add_obstacle(self, x, y):
+        return shim_namespace()["add_obstacle"](self, x, y)
+
+    def add_external_force(self, pos, pre_pos):
+        return shim_namespace()["add_external_force"](self, pos, pre_pos)
+
+
+class ShimSimulator:
+    """CudaFluidSimulator: the fields its `impl Simulator` host logic touches."""
+
+    def __init__(self, nx, ny, lattice_pixel_size, ty, info):
+        self.fluid_compute_node = ShimNode(nx, ny, lattice_pixel_size, ty, info)
+        self.lattice = self.fluid_compute_node.lattice
+        self.lattice_pixel_size = lattice_pixel_size
+        self.pre_pos = rt.Vec2(0.0, 0.0)
+
+    @property
+    def writes(self):
+        return self.fluid_compute_node.writes
+
+    def on_click(self, x, y):
+        shim_namespace()["on_click"](self, None, rt.Vec2(x, y))
+
+    def touch_begin(self):
+        shim_namespace()["touch_begin"](self, None)
+
+    def touch_move(self, x, y):
+        shim_namespace()["touch_move"](self, None, rt.Vec2(x, y))
+
+    def update_uniforms(self, viscosity, ty):
+        setting = types.SimpleNamespace(fluid_viscosity=F(viscosity), animation_type=animation(ty))
+        shim_namespace()["update_uniforms"](self, None, setting)

@@ -146,8 +146,26 @@ _F32_METHODS = {
 }
 
 
+def macro(name, *args):
+    if name == "panic":
+        raise RuntimeError("panic!: " + " ".join(str(a) for a in args))
+    if name == "assert_eq":
+        assert args[0] == args[1], args
+        return None
+    raise NotImplementedError(name + "!")
+
+
 def method(obj, name, *args):
+    if name in ("unwrap_or_else", "unwrap", "expect", "clone"):  # Result / Option = their success value here
+        return obj
+    if isinstance(obj, range):
+        if name == "contains":
+            return args[0] in obj
     if isinstance(obj, (np.floating, float)):
+        if name == "min":
+            return obj if obj < args[0] else F(args[0])  # f32::min (no NaN on this path)
+        if name == "max":
+            return obj if obj > args[0] else F(args[0])
         return _F32_METHODS[name](obj, *args)
     if isinstance(obj, list):
         if name == "push":

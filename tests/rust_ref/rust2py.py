@@ -206,10 +206,8 @@ class Parser:
             self.next()
             pat = self.pattern()
             self.expect("in")
-            lo = self.expr(no_struct=True, no_range=True)
-            self.expect("..")
-            hi = self.expr(no_struct=True, no_range=True)
-            return ("for", pat, lo, hi, self.block())
+            it = self.expr(no_struct=True)
+            return ("for", pat, it, self.block())
         if v == "continue" and k == "id":
             self.next()
             self.expect(";")
@@ -269,12 +267,17 @@ class Parser:
               ["*", "/", "%"]]
 
     def expr(self, level=0, no_struct=False, no_range=False):
+        if level == 0 and not no_range:  # a..b binds loosest
+            lo = self.expr(0, no_struct, True)
+            if self.accept(".."):
+                return ("range", lo, self.expr(0, no_struct, True))
+            return lo
         if level == len(self.LEVELS):
             return self.cast(no_struct)
-        lhs = self.expr(level + 1, no_struct, no_range)
+        lhs = self.expr(level + 1, no_struct, True)
         while self.peek()[0] == "op" and self.peek()[1] in self.LEVELS[level]:
             op = self.next()[1]
-            lhs = ("bin", op, lhs, self.expr(level + 1, no_struct, no_range))
+            lhs = ("bin", op, lhs, self.expr(level + 1, no_struct, True))
         return lhs
 
     def cast(self, no_struct):
@@ -312,6 +315,8 @@ class Parser:
                 e = ("index", e, idx)
             elif self.at("(") and e[0] in ("path", "name"):
                 e = ("call", e, self.args())
+            elif self.accept("?"):
+                pass  # Result / Option are modelled by their success value: errors do not occur on this path
             else:
                 return e
 
@@ -365,6 +370,13 @@ class Parser:
             return self.if_expr()
         if v == "match" and k == "id":
             return self.match_expr()
+        if v == "|" and k == "op":  # closure |a, b| expr
+            self.next()
+            params = []
+            while not self.accept("|"):
+                params.append(self.pattern())
+                self.accept(",")
+            return ("closure", params, self.expr(no_struct=no_struct))
         if v in ("true", "false") and k == "id":
             self.next()
             return ("bool", v == "true")
@@ -381,6 +393,9 @@ class Parser:
                     items.append(self.expr())
                     self.accept(",")
                 return ("array", items)
+            if self.at("!") and self.peek(1)[1] == "(":  # other macros (panic!, assert_eq!): name + arguments
+                self.next()
+                return ("macro", segs[-1], self.args())
             if self.at("{") and not no_struct and segs[-1][0].isupper():
                 self.next()
                 fields = []
@@ -433,8 +448,8 @@ class Emitter:
             elif k == "fn":
                 self.fn(s, ind)
             elif k == "for":
-                self.lines.append(f"{pad}for {self.pat(s[1])} in range({self.ex(s[2])}, {self.ex(s[3])}):")
-                self.block(s[4], ind + 1)
+                self.lines.append(f"{pad}for {self.pat(s[1])} in {self.ex(s[2])}:")
+                self.block(s[3], ind + 1)
             elif k == "continue":
                 self.lines.append(pad + "continue")
             elif k == "return":
@@ -529,7 +544,15 @@ class Emitter:
         if k == "field":
             return f"{self.ex(e[1])}.{pyname(e[2])}"
         if k == "index":
+            if e[2][0] == "range":
+                return f"{self.ex(e[1])}[{self.ex(e[2][1])}:{self.ex(e[2][2])}]"
             return f"{self.ex(e[1])}[{self.ex(e[2])}]"
+        if k == "range":
+            return f"range({self.ex(e[1])}, {self.ex(e[2])})"
+        if k == "closure":
+            return "(lambda " + ", ".join(self.pat(p) for p in e[1]) + ": " + self.ex(e[2]) + ")"
+        if k == "macro":
+            return f"_rt.macro({e[1]!r}" + "".join(", " + self.ex(a) for a in e[2]) + ")"
         if k == "method":
             return f"_rt.method({self.ex(e[1])}, {e[2]!r}" + "".join(", " + self.ex(a) for a in e[3]) + ")"
         if k == "call":

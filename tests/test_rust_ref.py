@@ -162,3 +162,37 @@ def test_live_execution_of_the_rust_source_matches_the_golden():
         sim.touch_move(*pos)
     assert [w[1] for w in sim.writes] == [int(o) for o in G["drag_offsets"]]
     assert b"".join(w[2] for w in sim.writes) == G["drag_cells"].tobytes()
+
+
+def test_the_repos_rust_shim_executed_leaves_the_reference_writes():
+    """rust/simuverse-cuda-lbm (CudaD2Q9Node / CudaFluidSimulator) is shipped as source that this image cannot compile.
+    Its host logic — written independently of the reference's wording — is executed by the same Rust-subset interpreter,
+    with the FFI calls replaced by recorders: clicks, the drag and the uniform updates of the golden must leave exactly
+    the writes the reference's own Rust text leaves."""
+    from rust_ref import harness as H
+
+    if not H.available():
+        pytest.skip("reference tree not present (the shim imports the reference's own helper items)")
+    sim = H.ShimSimulator(NX, NY, LPS, W.POISEUILLE, G["mask_0"])
+    for v, ty in G["viscosities"]:
+        sim.update_uniforms(v, int(ty))
+    assert b"".join(w[2] for w in sim.writes) == G["update_uniform_bytes"].tobytes()
+    del sim.writes[:]
+    k = 0
+    for pos, wrote in zip(G["clicks"], G["click_wrote"]):
+        n0 = len(sim.writes)
+        sim.on_click(*pos)
+        assert (len(sim.writes) > n0) == bool(wrote)
+        if wrote:
+            assert sim.writes[-1] == ("info_buf", int(G["click_offsets"][k]), G["click_patches"][k].tobytes())
+            k += 1
+    assert H.info_to_array(sim.fluid_compute_node.lattice_info_data).tobytes() == G["mirror_after_clicks"].tobytes()
+    del sim.writes[:]
+    sim.touch_begin()
+    for pos, count, want_pre in zip(G["drag"], G["drag_write_counts"], G["drag_pre_pos"]):
+        n0 = len(sim.writes)
+        sim.touch_move(*pos)
+        assert len(sim.writes) - n0 == int(count)
+        assert (sim.pre_pos.x, sim.pre_pos.y) == tuple(want_pre)
+    assert [w[1] for w in sim.writes] == [int(o) for o in G["drag_offsets"]]
+    assert b"".join(w[2] for w in sim.writes) == G["drag_cells"].tobytes()
