@@ -434,6 +434,26 @@ int fuse_geometry(LbmSim *s) {
     CU(cudaMemcpy(s->d_fuse_rows, items0.data(), sizeof(int2) * items0.size(), cudaMemcpyHostToDevice));
     g.items = s->d_fuse_rows;
     g.negzero2 = 0x8000000080000000ull;
+    g.pack_a = g.pack_n = 0;
+#if LBM_FUSE_PACK
+    // The last CTA column holds strips % kFuseWarps strips.  With one or two (4096 columns: 69 strips = 17 CTAs + ONE
+    // strip) its CTAs would keep the registers of four warps for the work of one: they take four (two) row blocks instead
+    // (4096^2: 126.8 -> 132.6 GLUPS, 8192^2 porous 72.8 -> 75.1, 16384^2 +1.4 %; profiles/r02_s3_experiments.md).  Not on a
+    // lattice that fits the GPU in one wave (nothing competes for the slots), nor on slabs (the edge-block bookkeeping of
+    // the neighbour protocol is per CTA).
+    {
+        const int a = g.strips % kFuseWarps;
+        const bool on = getenv("LBM_FUSE_PACK") ? atoi(getenv("LBM_FUSE_PACK")) != 0 : true;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
+        const long long resident = (long long)sms * LBM_FUSE_MIN_CTAS;
+        const long long blocks = (long long)g.rowblocks0 + (long long)g.rowblocks * (g.ctas_x - 1);
+        if (on && s->d.world == 1 && g.ctas_x >= 3 && a != 0 && kFuseWarps % a == 0 && a < kFuseWarps && blocks > resident) {
+            g.pack_a = a;
+            g.pack_n = (g.rowblocks + kFuseWarps / a - 1) / (kFuseWarps / a);
+        }
+    }
+#endif
     return LBM_OK;
 }
 
@@ -532,7 +552,7 @@ void launch_frame2(const LbmSim *s, unsigned int grid, int first, int macro) {
 // stores the field of t+2 into it; mid_texture: also the field of t+1 into s->macro_mid (frames with tracer particles).
 int launch_pair(LbmSim *s, int first, bool mid_texture = false) {
     const FuseGeom &g = s->fuse;
-    const long long blocks = (long long)g.rowblocks0 + (long long)g.rowblocks * (g.ctas_x - 1);
+    const long long blocks = (long long)g.rowblocks0 + g.pack_n + (long long)g.rowblocks * (g.ctas_x - 1 - (g.pack_n ? 1 : 0));
     if (blocks > 2147483647ll) return fail(s, LBM_ERR_INVALID_ARG, "lattice too large for one sweep launch");
     // rho * w is shared between the directions of equal weight when the uploaded weights allow it
     const Coef &k = s->P.k;
