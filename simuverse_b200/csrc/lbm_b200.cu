@@ -356,13 +356,20 @@ int fuse_geometry(LbmSim *s) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
         if (s->d.world > 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, true, 0, false>, kFuseThreads, 0);
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame2<true, false, 0, false>, kFuseThreads, 0);
-        // Uniform height giving at least ~6 waves of CTAs (measured on B200: with fewer the sweep ends in a long
-        // tail; 4096^2 is best at 16 rows, 16384^2 at 32), between 8 and 32 rows.
-        int h_min = 8, h_max = 32;
+        // Uniform height giving at least ~6 waves of CTAs, between 8 and 32 rows (measured on B200 in rounds 1 / 2: with
+        // fewer waves the sweep ended in a long tail; 4096^2 best at 16 rows, 16384^2 at 32).  Single slab, since the
+        // packed last column (below) took the partially filled CTAs out of that tail: ~3 waves and up to 64 rows — taller
+        // blocks, less redundant work — with the last wave cut at quarter height (4096^2 at 32 rows 132.6 -> 136.3 GLUPS,
+        // 16384^2 at 64 rows +1.8 %; profiles/r02_s3_experiments.md).  Slabs keep the rule they were measured with.
+        const bool tall = s->d.world == 1 && LBM_FUSE_PACK;
+        // (64-row blocks paid only on 64 KB rows: 16384^2 +1.8 %, but 8192^2 porous 76.1 -> 74.6 GLUPS)
+        int h_min = 8, h_max = (tall && (long long)s->P.pitch * 4 >= 65536) ? 64 : 32;
         if (const char *e = getenv("LBM_FUSE_HMIN")) h_min = std::max(1, atoi(e));
         if (const char *e = getenv("LBM_FUSE_HMAX")) h_max = std::max(h_min, atoi(e));
+        int waves = tall ? 3 : 6;
+        if (const char *e = getenv("LBM_FUSE_WAVES")) waves = std::max(1, atoi(e));
         const long long resident = (long long)sms * std::max(per_sm, 1);
-        H = (int)((long long)h * g.ctas_x / (6 * resident));
+        H = (int)((long long)h * g.ctas_x / (waves * resident));
         H = std::max(h_min, std::min(H, h_max));
         // A lattice too small to fill the GPU even once at h_min rows per block (the reference's own 600 x 375) is
         // bound by the latency of a block's serial march, (H + 2) row iterations: the shortest blocks that still fit
@@ -377,8 +384,10 @@ int fuse_geometry(LbmSim *s) {
         if (page % row_bytes == 0 && (s->P.plane * 4) % page == 0) {
             const int rpp = (int)(page / row_bytes);
             int best = 0;
-            for (int c = rpp; c >= h_min; c >>= 1) {
-                if (c > h_max || (rpp % c) != 0) continue;
+            int top = rpp; // power-of-two fractions of a page, and whole pages when a page holds fewer rows than h_max
+            while (top * 2 <= h_max) top *= 2;
+            for (int c = top; c >= h_min; c >>= 1) {
+                if (c > h_max || (c <= rpp ? (rpp % c) != 0 : (c % rpp) != 0)) continue;
                 if (!best || std::abs(c - H) < std::abs(best - H)) best = c;
             }
             if (best) H = best;
@@ -390,7 +399,7 @@ int fuse_geometry(LbmSim *s) {
     // Tail shaping: when the grid is only a few waves long, the rows dispatched last — about one wave of CTAs — are cut
     // at half height, so that the sweep ends with short work items instead of a ragged last wave (4096^2: 6.6 waves,
     // SMs active 91 % of the launch without it).  LBM_FUSE_TAIL=0 turns it off.
-    int tail_rows = 0, tail_div = 2;
+    int tail_rows = 0, tail_div = (s->d.world == 1 && LBM_FUSE_PACK) ? 4 : 2;
     double tail_waves = 1.0;
     {
         int sms = 148, per_sm = LBM_FUSE_MIN_CTAS;
@@ -439,16 +448,18 @@ int fuse_geometry(LbmSim *s) {
     // The last CTA column holds strips % kFuseWarps strips.  With one or two (4096 columns: 69 strips = 17 CTAs + ONE
     // strip) its CTAs would keep the registers of four warps for the work of one: they take four (two) row blocks instead
     // (4096^2: 126.8 -> 132.6 GLUPS, 8192^2 porous 72.8 -> 75.1, 16384^2 +1.4 %; profiles/r02_s3_experiments.md).  Not on a
-    // lattice that fits the GPU in one wave (nothing competes for the slots), nor on slabs (the edge-block bookkeeping of
-    // the neighbour protocol is per CTA).
+    // lattice that fits the GPU in one wave (nothing competes for the slots).  On slabs too (a 16384 x 2048 slab: 140.0 ->
+    // 143.4 GLUPS): the first packed CTA holds the edge row blocks, it waits for the neighbours as a whole and each of its
+    // warps signals for its own row block (frame2_is_edge).
     {
         const int a = g.strips % kFuseWarps;
-        const bool on = getenv("LBM_FUSE_PACK") ? atoi(getenv("LBM_FUSE_PACK")) != 0 : true;
+        const int knob = getenv("LBM_FUSE_PACK") ? atoi(getenv("LBM_FUSE_PACK")) : 1; // 0 off, 2 = also on one-wave lattices (tests)
+        const bool on = knob != 0;
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device);
         const long long resident = (long long)sms * LBM_FUSE_MIN_CTAS;
         const long long blocks = (long long)g.rowblocks0 + (long long)g.rowblocks * (g.ctas_x - 1);
-        if (on && s->d.world == 1 && g.ctas_x >= 3 && a != 0 && kFuseWarps % a == 0 && a < kFuseWarps && blocks > resident) {
+        if (on && g.ctas_x >= 3 && a != 0 && kFuseWarps % a == 0 && a < kFuseWarps && (blocks > resident || knob == 2)) {
             g.pack_a = a;
             g.pack_n = (g.rowblocks + kFuseWarps / a - 1) / (kFuseWarps / a);
         }

@@ -364,3 +364,41 @@ def test_divergent_fallback_paths_on_a_wide_lattice(orc, preset, solid):
     assert a.fused_sweep_count == 18 and b.fused_sweep_count == 0
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("nx,n_slabs,rows", [(520, 1, 0), (520, 3, 0), (760, 2, 0), (520, 4, 4), (1000, 1, 3)])
+def test_packed_last_strip_column(orc, monkeypatch, nx, n_slabs, rows):
+    """The last CTA column of a sweep holds one or two strips at these widths (520 -> 9 strips, 760 -> 13 -> one; 1000 -> 17 ->
+    one): its CTAs take four / two row blocks each (FuseGeom::pack_a).  LBM_FUSE_PACK=2 forces the packing on lattices
+    that fit in one wave, where it is normally off; on slabs the first packed CTA holds the edge row blocks: it waits
+    for the neighbours as a whole and every warp signals for its own row block."""
+    from simuverse_b200.slabs import SlabGroup
+
+    monkeypatch.setenv("LBM_FUSE_PACK", "2")
+    if rows:
+        monkeypatch.setenv("LBM_FUSE_ROWS", str(rows))
+    ny = 96
+    info = random_mask(orc, nx, ny, W.POISEUILLE, seed=nx + n_slabs, solid=0.04)
+    g = info.reshape(ny, nx)
+    for cut in range(1, n_slabs):  # solids and force cells on the cuts, also inside the last strip column
+        y = ny * cut // n_slabs
+        g["material"][y - 2:y + 2, nx - 40:nx - 25] = W.OBSTACLE
+        g[y, nx - 12] = (W.EXTERNAL_FORCE, -1, 0.04, -0.06)
+        g[y - 1, nx - 50] = (W.EXTERNAL_FORCE, -1, -0.05, 0.03)
+    sim = oracle_for(orc, nx, ny, W.POISEUILLE, info)
+    if n_slabs == 1:
+        a = node_for(nx, ny, W.POISEUILLE, info)
+        nodes = [a]
+    else:
+        a = SlabGroup((nx * 2, ny * 2), setting(W.POISEUILLE), lattice=(nx, ny), n_slabs=n_slabs, lattice_info=info)
+        nodes = a.nodes
+    total = 0
+    for n in (2, 7, 40):
+        a.step_n(n)
+        sim.step(n)
+        total += n
+        for which in (0, 1):
+            assert_bits_equal(a.read_distributions(which), sim.distributions(which), f"{nx} wide, {n_slabs} slab(s), {total} updates, buf{which}")
+        assert_bits_equal(a.read_macro(), sim.macro(), f"{total} updates, macro")
+    assert all(n.fused_sweep_count == 24 for n in nodes), [n.fused_sweep_count for n in nodes]
+    a.close()
