@@ -680,7 +680,7 @@ size_t orc_add_external_force(int32_t nx, int32_t ny, uint32_t lattice_pixel_siz
     return n;
 }
 
-/* d2q9_node.rs:65-76 */
+/* d2q9_node.rs:61-76 */
 void orc_field_uniform_new(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, int32_t canvas_w,
                            int32_t canvas_h, FieldUniform *out) {
     memset(out, 0, sizeof(*out));
@@ -690,6 +690,16 @@ void orc_field_uniform_new(int32_t nx, int32_t ny, uint32_t lattice_pixel_size, 
     out->lattice_pixel_size[1] = (float)lattice_pixel_size;
     out->canvas_size[0] = canvas_w;
     out->canvas_size[1] = canvas_h;
+    /* (_, sx, sy) = fullscreen_factor((canvas_w, canvas_h), fovy), util/matrix_helper.rs:19-41: the longer side over
+     * the shorter one on its axis, 1 on the other; proj_ratio = [sx, sy], ndc_pixel = [sx * 2.0 / w, sy * 2.0 / h] */
+    {
+        float vw = (float)canvas_w, vh = (float)canvas_h, sx = 1.0f, sy = 1.0f;
+        if (vh > vw) sy = vh / vw; else sx = vw / vh;
+        out->proj_ratio[0] = sx;
+        out->proj_ratio[1] = sy;
+        out->ndc_pixel[0] = sx * 2.0f / vw;
+        out->ndc_pixel[1] = sy * 2.0f / vh;
+    }
     out->speed_ty = 1;
 }
 

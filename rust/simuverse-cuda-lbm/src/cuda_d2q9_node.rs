@@ -90,12 +90,17 @@ impl CudaD2Q9Node {
         let fluid_ty = (setting.animation_type == FieldAnimationType::LidDrivenCavity) as i32;
         let tau = 3.0 * setting.fluid_viscosity + 0.5; // d2q9_node.rs:50
         let lbm_uniform_data = LbmUniform::new(tau, fluid_ty, (lattice.width * lattice.height) as i32);
+        // d2q9_node.rs:61-64 (no LBM shader reads proj_ratio / ndc_pixel, but they are part of the reference's 48 bytes)
+        let (_, sx, sy) = crate::util::matrix_helper::fullscreen_factor(
+            (canvas_size.x as f32, canvas_size.y as f32).into(),
+            75.0 / 180.0 * core::f32::consts::PI,
+        );
         let field_uniform_data = FieldUniform {
             lattice_size: [lattice.width as i32, lattice.height as i32],
             lattice_pixel_size: [lattice_pixel_size as f32; 2],
             canvas_size: [canvas_size.x as i32, canvas_size.y as i32],
-            proj_ratio: [0.0; 2], // render-only (util/matrix_helper.rs fullscreen_factor)
-            ndc_pixel: [0.0; 2],
+            proj_ratio: [sx, sy],
+            ndc_pixel: [sx * 2.0 / canvas_size.x as f32, sy * 2.0 / canvas_size.y as f32],
             speed_ty: 1,
             _padding: 0.0,
         };

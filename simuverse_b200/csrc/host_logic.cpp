@@ -101,6 +101,15 @@ extern "C" void lbm_field_uniform_new(int32_t nx, int32_t ny, uint32_t lattice_p
     f.lattice_pixel_size[0] = f.lattice_pixel_size[1] = static_cast<float>(lattice_pixel_size);
     f.canvas_size[0] = canvas_w;
     f.canvas_size[1] = canvas_h;
+    // proj_ratio / ndc_pixel (d2q9_node.rs:61-73 with util/matrix_helper.rs:27-37 fullscreen_factor): no LBM shader reads
+    // them (they feed the field simulator's velocity code), but they are part of the 48 bytes the reference uploads
+    const float vw = static_cast<float>(canvas_w), vh = static_cast<float>(canvas_h);
+    float sx = 1.0f, sy = 1.0f;
+    if (vh > vw) sy = vh / vw; else sx = vw / vh;
+    f.proj_ratio[0] = sx;
+    f.proj_ratio[1] = sy;
+    f.ndc_pixel[0] = sx * 2.0f / vw;
+    f.ndc_pixel[1] = sy * 2.0f / vh;
     f.speed_ty = 1;
     *out = f;
 }

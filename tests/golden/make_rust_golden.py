@@ -8,6 +8,7 @@
     touch_begin / touch_move -> add_external_force (fluid_simulator.rs:154-173, d2q9_node.rs:263-300)   a drag: pre_pos
                                                             bookkeeping and every 16-byte write
     get_particles_data (lib.rs:247-273)                     tracer grid extent + workgroup count
+    fullscreen_factor + the FieldUniform literal (util/matrix_helper.rs:19-41, d2q9_node.rs:61-76)   the 48 uniform bytes
 
 Needs /root/reference (build container only); the output is committed.
 Run from the repo root:  python tests/golden/make_rust_golden.py
@@ -82,6 +83,10 @@ def main():
     out["drag_offsets"] = np.array([w[1] for w in sim.writes], np.uint64)
     out["drag_cells"] = np.frombuffer(b"".join(w[2] for w in sim.writes), H.LATTICE_INFO_DTYPE)
     print("drag writes per move:", counts)
+    # FieldUniform as D2Q9Node::new builds it (d2q9_node.rs:38-76 + util/matrix_helper.rs:19-41)
+    fields = [(1200, 750, 2), (750, 1200, 2), (2400, 1500, 4), (800, 800, 2), (333, 777, 3), (32768, 32768, 2)]
+    out["field_args"] = np.array(fields, np.int32)
+    out["field_bytes"] = np.frombuffer(b"".join(H.field_uniform(*f) for f in fields), np.uint8)
     # tracer grid (lib.rs:247-264)
     grids = [(1200, 750, 10000), (1200, 750, 205000), (2400, 1500, 40000), (800, 800, 1000), (333, 777, 5000),
              (16384, 16384, 1000000)]

@@ -7,6 +7,7 @@ them to stand-ins for the objects they touch (`self`, `queue`, `app`, `setting`)
     fluid/d2q9_node.rs       add_obstacle (:215-245), add_external_force (:263-300)
     fluid/fluid_simulator.rs on_click (:137-152), touch_begin (:154-156), touch_move (:158-173),
                              update_uniforms (:175-193)
+    util/matrix_helper.rs    fullscreen_factor (:19-41), and the FieldUniform literal of D2Q9Node::new (d2q9_node.rs:61-76)
     lib.rs                   get_particles_data (:247-273): the tracer grid extent and workgroup count (its call of
                              init_trajectory_particles, which draws from an unseeded rand::rng(), is stubbed out)
 """
@@ -50,6 +51,12 @@ def namespace():
         code.append(rust2py.transpile_fn(rust2py.extract_fn(node, fn)))
     for fn in ("on_click", "touch_begin", "touch_move", "update_uniforms"):
         code.append(rust2py.transpile_fn(rust2py.extract_fn(sim, fn)))
+    util = open(os.path.join(os.path.dirname(SRC), "util", "matrix_helper.rs"), encoding="utf-8").read()
+    code.append(rust2py.transpile_fn(rust2py.extract_fn(util, "fullscreen_factor")))
+    # the FieldUniform literal of D2Q9Node::new (d2q9_node.rs:65-76), as an expression of lattice / lattice_pixel_size /
+    # canvas_size / sx / sy
+    code.append("def field_uniform_literal(lattice, lattice_pixel_size, canvas_size, sx, sy):\n    return "
+                + rust2py.transpile_expr(rust2py.extract_let(node, "field_uniform_data")) + "\n")
     lib_rs = open(os.path.join(os.path.dirname(SRC), "lib.rs"), encoding="utf-8").read()
     code.append(rust2py.transpile_const(rust2py.extract_item(lib_rs, "const", "MAX_PARTICLE_COUNT")))
     code.append(rust2py.transpile_fn(rust2py.extract_fn(lib_rs, "get_particles_data")))
@@ -249,3 +256,21 @@ class ShimSimulator:
     def update_uniforms(self, viscosity, ty):
         setting = types.SimpleNamespace(fluid_viscosity=F(viscosity), animation_type=animation(ty))
         shim_namespace()["update_uniforms"](self, None, setting)
+
+
+def field_uniform(canvas_w, canvas_h, lattice_pixel_size):
+    """The 48 bytes of FieldUniform as D2Q9Node::new builds them (d2q9_node.rs:38-76): lattice = canvas / lattice_pixel_size,
+    (sx, sy) from util::matrix_helper::fullscreen_factor(canvas, 75 deg)."""
+    ns = namespace()
+    canvas = types.SimpleNamespace(x=int(canvas_w), y=int(canvas_h))
+    lattice = types.SimpleNamespace(width=canvas.x // lattice_pixel_size, height=canvas.y // lattice_pixel_size,
+                                    depth_or_array_layers=1)
+    pi = F(np.pi)  # core::f32::consts::PI
+    fovy = F(F(F(75.0) / F(180.0)) * pi)
+    _, sx, sy = ns["fullscreen_factor"](rt.Vec2(F(canvas.x), F(canvas.y)), fovy)
+    u = ns["field_uniform_literal"](lattice, int(lattice_pixel_size), canvas, sx, sy)
+    b = struct.pack("<2i", *[int(v) for v in u.lattice_size]) + struct.pack("<2f", *[float(F(v)) for v in u.lattice_pixel_size])
+    b += struct.pack("<2i", *[int(v) for v in u.canvas_size]) + struct.pack("<2f", *[float(F(v)) for v in u.proj_ratio])
+    b += struct.pack("<2f", *[float(F(v)) for v in u.ndc_pixel]) + struct.pack("<if", int(u.speed_ty), float(F(u._padding)))
+    assert len(b) == 48
+    return b

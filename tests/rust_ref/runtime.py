@@ -17,7 +17,7 @@ import numpy as np
 F = np.float32
 
 _libm = ctypes.CDLL(ctypes.util.find_library("m") or "libm.so.6")
-for _n, _argc in (("atan2f", 2), ("cosf", 1), ("sinf", 1), ("roundf", 1), ("ceilf", 1), ("floorf", 1)):
+for _n, _argc in (("atan2f", 2), ("cosf", 1), ("sinf", 1), ("tanf", 1), ("roundf", 1), ("ceilf", 1), ("floorf", 1)):
     getattr(_libm, _n).restype = ctypes.c_float
     getattr(_libm, _n).argtypes = [ctypes.c_float] * _argc
 
@@ -138,6 +138,7 @@ _F32_METHODS = {
     "atan2": lambda y, x: _m("atan2f", y, x),
     "cos": lambda a: _m("cosf", a),
     "sin": lambda a: _m("sinf", a),
+    "tan": lambda a: _m("tanf", a),
     "round": lambda a: _m("roundf", a),
     "ceil": lambda a: _m("ceilf", a),
     "floor": lambda a: _m("floorf", a),

@@ -443,6 +443,10 @@ class Emitter:
             if k == "let":
                 if s[2] is None:
                     self.lines.append(f"{pad}{self.pat(s[1])} = None")
+                elif s[2][0] == "if" and not self.is_simple_if(s[2]):   # let x = if c { stmts; v } else { stmts; w };
+                    self.if_stmt(s[2], ind, self.pat(s[1]))
+                elif s[2][0] == "match":
+                    self.match_stmt(s[2], ind, self.pat(s[1]))
                 else:
                     self.lines.append(f"{pad}{self.pat(s[1])} = {self.ex(s[2])}")
             elif k == "fn":
@@ -593,3 +597,27 @@ def parse_enum(src):
 def transpile_const(src):
     _, name, expr = Parser(tokenize(src)).const()
     return f"{name} = {Emitter().ex(expr)}\n"
+
+
+def extract_let(text, name):
+    """Initialiser expression text of the first `let [mut] name [: T] = <expr>;` (balanced brackets up to the `;`)."""
+    m = re.search(r"\blet\s+(?:mut\s+)?" + re.escape(name) + r"\b[^=;]*=", text)
+    if not m:
+        raise KeyError(name)
+    depth, j = 0, m.end()
+    while j < len(text):
+        c = text[j]
+        if c in "({[":
+            depth += 1
+        elif c in ")}]":
+            depth -= 1
+        elif c == ";" and depth == 0:
+            return text[m.end():j]
+        j += 1
+    raise SyntaxError("unterminated let " + name)
+
+
+def transpile_expr(src):
+    p = Parser(tokenize(src))
+    e = p.expr()
+    return Emitter().ex(e)

@@ -139,6 +139,19 @@ def test_particle_grid_matches_executed_rust(orc):
         assert (-(-extent[0] // 16), -(-extent[1] // 16), 1) == tuple(groups)
 
 
+def test_field_uniform_matches_executed_rust(orc):
+    """FieldUniform as D2Q9Node::new builds it (d2q9_node.rs:38-76, util/matrix_helper.rs:19-41): all 48 bytes, including
+    proj_ratio / ndc_pixel, which no LBM shader reads — executing the reference's text is what showed that the oracle and
+    the product used to leave them at zero."""
+    for k, (cw, ch, lps) in enumerate(G["field_args"]):
+        want = G["field_bytes"].tobytes()[48 * k:48 * (k + 1)]
+        nx, ny = int(cw) // int(lps), int(ch) // int(lps)
+        assert bytes(orc.field_uniform_new(nx, ny, int(lps), int(cw), int(ch))) == want
+        f = W.FieldUniform()
+        sb.lib.lbm_field_uniform_new(nx, ny, int(lps), int(cw), int(ch), C.byref(f))
+        assert bytes(f) == want
+
+
 def test_live_execution_of_the_rust_source_matches_the_golden():
     """Re-executes the reference's Rust text when the tree is present (build container): small masks, one click, the drag."""
     from rust_ref import harness as H
@@ -152,6 +165,8 @@ def test_live_execution_of_the_rust_source_matches_the_golden():
         assert H.uniform_new(tau, int(ty), int(n)) == G["uniform_bytes"].tobytes()[304 * k:304 * (k + 1)]
     for (w, h, count), extent in zip(G["grid_args"], G["grid_extent"]):
         assert H.particle_grid(int(w), int(h), int(count))[0] == tuple(extent)
+    for k, (cw, ch, lps) in enumerate(G["field_args"]):
+        assert H.field_uniform(int(cw), int(ch), int(lps)) == G["field_bytes"].tobytes()[48 * k:48 * (k + 1)]
     sim = H.Simulator(NX, NY, LPS, W.POISEUILLE, G["mask_0"])
     first = int(np.nonzero(G["click_wrote"])[0][0])
     sim.on_click(*G["clicks"][first])
