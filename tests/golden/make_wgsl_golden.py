@@ -62,6 +62,13 @@ def case_cavity():
     return dict(nx=nx, ny=ny, fluid_ty=1, info=init_lattice_material(nx, ny, W.LID_DRIVEN_CAVITY), steps=40, post=[])
 
 
+def case_cavity100():
+    """The lid-driven cavity (fluid_ty = 1: the other init branch, ghost row wrapping onto a solid row, a whole row of force
+    cells) carried to north_star's "after 100 steps" too, on an odd-sized lattice."""
+    nx, ny = 46, 38
+    return dict(nx=nx, ny=ny, fluid_ty=1, info=init_lattice_material(nx, ny, W.LID_DRIVEN_CAVITY), steps=100, post=[])
+
+
 def case_force():
     nx, ny = 36, 30
     info = init_lattice_material(nx, ny, W.CUSTOM)
@@ -101,7 +108,8 @@ def case_midrun():
 
 CASES = {"wgsl_midrun_48x36_s44": case_midrun, "wgsl_channel_72x48_s40": case_channel, "wgsl_cavity_40x32_s40": case_cavity,
          "wgsl_force_36x30_s100": case_force, "wgsl_periodic_22x14_s30": case_periodic,
-         "wgsl_particles_60x40_f20": case_particles, "wgsl_channel100_64x48_s100": case_channel100}
+         "wgsl_particles_60x40_f20": case_particles, "wgsl_channel100_64x48_s100": case_channel100,
+         "wgsl_cavity100_46x38_s100": case_cavity100}
 
 
 def main():
